@@ -1,0 +1,534 @@
+// jss_api.cu -- the C-ABI of include/jss_b200.h on top of the sm_100a kernels in
+// jss_device.cuh.  Host side only does: validation, packing of the instance tables,
+// grouping envs into per-instance tiles, buffer ownership and kernel launches.
+// There is no CPU implementation of the environment in this library.
+#ifdef JSS_EMU
+#include "cuda_shim.h"  // tests/emu: TEST-ONLY host emulation, never defined for the product build
+#else
+#include <cuda_runtime.h>
+#define JSS_SMEM_DECL(name) extern __shared__ uint4 name[]
+#define JSS_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
+#include <algorithm>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "jss_device.cuh"
+
+namespace {
+
+std::string g_create_error;
+
+struct HostInst {
+    int J, M;
+    int64_t max_time_op, max_time_jobs, sum_op;
+};
+
+}  // namespace
+
+struct jss_handle {
+    int device = -1;
+    int n_envs = 0;
+    uint32_t create_flags = 0;
+    uint64_t env_id_base = 0;
+    int sm_count = 0;
+    std::string err;
+    int64_t launches = 0;
+
+    std::vector<HostInst> insts;
+    std::vector<JssInstDesc> descs;
+    bool loaded = false, assigned = false;
+
+    // device allocations
+    std::vector<void *> allocs;
+    JssInstDesc *d_inst = nullptr;
+    uint16_t *d_ops = nullptr, *d_rem = nullptr;
+    int32_t *d_len = nullptr;
+    unsigned long long *d_stats = nullptr;
+
+    JssParams p{};
+    JssSmemLayout sl_norem{}, sl_rem{};
+    int class_tile_begin[3] = {0, 0, 0}, class_tile_end[3] = {0, 0, 0};  // KJ = 1, 2, 4
+    std::vector<int32_t> env_inst;
+
+    // pinned staging for jss_step_host
+    int32_t *pin_actions = nullptr;
+    int32_t *dev_actions = nullptr;
+};
+
+namespace {
+
+int fail(jss_t *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define JSS_CUDA(h, expr)                                                                           \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail((h), JSS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),  \
+                        __FILE__, __LINE__);                                                        \
+    } while (0)
+
+template <typename T>
+int dev_alloc(jss_t *h, T **out, size_t count, bool zero = true) {
+    void *ptr = nullptr;
+    const size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    JSS_CUDA(h, cudaMalloc(&ptr, bytes));
+    h->allocs.push_back(ptr);
+    if (zero) JSS_CUDA(h, cudaMemset(ptr, 0, bytes));
+    *out = static_cast<T *>(ptr);
+    return JSS_OK;
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline int kj_of(int J) { return J <= 32 ? 1 : (J <= 64 ? 2 : 4); }
+inline int class_of(int kj) { return kj == 1 ? 0 : (kj == 2 ? 1 : 2); }
+
+size_t smem_bytes(const JssSmemLayout &sl) {
+    return (size_t)sl.ops_elems * 2 + (size_t)sl.len_elems * 4 + (size_t)sl.rem_elems * 2 +
+           (size_t)JSS_WARPS_PER_CTA * sl.scratch_words * 4;
+}
+
+template <int KJ>
+int launch_class(jss_t *h, const JssLaunch &a, const JssSmemLayout &sl, cudaStream_t st) {
+    const int n_tiles = a.tile_end - a.tile_begin;
+    if (n_tiles <= 0) return JSS_OK;
+    const size_t smem = smem_bytes(sl);
+    int per_sm = 0;
+    JSS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jss_env_kernel<KJ>,
+                                                               JSS_WARPS_PER_CTA * 32, smem));
+    if (per_sm < 1) return fail(h, JSS_ERR_CUDA, "kernel does not fit on an SM (smem %zu B)", smem);
+    const int grid = std::min(n_tiles, h->sm_count * per_sm);
+    JSS_LAUNCH(jss_env_kernel<KJ>, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl);
+    JSS_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    return JSS_OK;
+}
+
+int launch_all(jss_t *h, JssLaunch a, bool want_rem, cudaStream_t st) {
+    const JssSmemLayout &sl = want_rem ? h->sl_rem : h->sl_norem;
+    for (int c = 0; c < 3; c++) {
+        a.tile_begin = h->class_tile_begin[c];
+        a.tile_end = h->class_tile_end[c];
+        int rc = JSS_OK;
+        if (c == 0) rc = launch_class<1>(h, a, sl, st);
+        else if (c == 1) rc = launch_class<2>(h, a, sl, st);
+        else rc = launch_class<4>(h, a, sl, st);
+        if (rc != JSS_OK) return rc;
+    }
+    return JSS_OK;
+}
+
+bool rule_wants_rem(int rule) { return rule == JSS_RULE_MWR || rule == JSS_RULE_LWR || rule == JSS_RULE_CR; }
+
+int check_ready(jss_t *h) {
+    if (!h) return JSS_ERR_INVALID;
+    if (!h->assigned) return fail(h, JSS_ERR_STATE, "jss_load_instances + jss_assign must be called first");
+    JSS_CUDA(h, cudaSetDevice(h->device));
+    return JSS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jss_abi_version(void) { return JSS_ABI_VERSION; }
+
+const char *jss_last_error(const jss_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t jss_launch_count(const jss_t *h) { return h ? h->launches : 0; }
+
+int jss_create(jss_t **out, int device, int n_envs, uint32_t flags, uint64_t env_id_base) {
+    if (!out || n_envs <= 0) return fail(nullptr, JSS_ERR_INVALID, "jss_create: bad arguments");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, JSS_ERR_NO_DEVICE,
+                    "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev)
+        return fail(nullptr, JSS_ERR_NO_DEVICE, "device %d out of range (have %d)", device, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return fail(nullptr, JSS_ERR_NO_DEVICE, "cudaGetDeviceProperties failed");
+    if (prop.major < 10)
+        return fail(nullptr, JSS_ERR_NO_DEVICE, "device %d is sm_%d%d; this build targets sm_100a (B200)", device,
+                    prop.major, prop.minor);
+    jss_t *h = new jss_handle();
+    h->device = device;
+    h->n_envs = n_envs;
+    h->create_flags = flags;
+    h->env_id_base = env_id_base;
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, JSS_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    }
+    *out = h;
+    return JSS_OK;
+}
+
+void jss_destroy(jss_t *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (void *ptr : h->allocs) cudaFree(ptr);
+    if (h->pin_actions) cudaFreeHost(h->pin_actions);
+    delete h;
+}
+
+int jss_load_instances(jss_t *h, int n_inst, const int32_t *jobs, const int32_t *machines, const int64_t *offsets,
+                       const int32_t *machine, const int32_t *duration) {
+    if (!h || n_inst <= 0 || !jobs || !machines || !offsets || !machine || !duration)
+        return fail(h, JSS_ERR_INVALID, "jss_load_instances: bad arguments");
+    if (h->loaded) return fail(h, JSS_ERR_STATE, "instances already loaded");
+    if (n_inst >= (1 << 23)) return fail(h, JSS_ERR_UNSUPPORTED, "too many instances");
+    JSS_CUDA(h, cudaSetDevice(h->device));
+    std::vector<uint16_t> ops, rem;
+    std::vector<int32_t> len;
+    h->insts.resize(n_inst);
+    h->descs.resize(n_inst);
+    for (int k = 0; k < n_inst; k++) {
+        const int J = jobs[k], M = machines[k];
+        if (J <= 0 || M <= 1)  // asserts at jss_env.py:93-94
+            return fail(h, JSS_ERR_INVALID, "instance %d: need jobs > 0 and machines > 1 (got %dx%d)", k, J, M);
+        if (J > JSS_MAX_JOBS || M > JSS_MAX_MACHINES)
+            return fail(h, JSS_ERR_UNSUPPORTED, "instance %d: %dx%d exceeds the %dx%d kernel limit", k, J, M,
+                        JSS_MAX_JOBS, JSS_MAX_MACHINES);
+        const int32_t *mm = machine + offsets[k], *dd = duration + offsets[k];
+        HostInst hi{J, M, 0, 0, 0};
+        JssInstDesc d{};
+        d.J = J; d.M = M;
+        d.ops_off = (int32_t)ops.size();
+        d.len_off = (int32_t)len.size();
+        d.rem_off = (int32_t)rem.size();
+        ops.resize(ops.size() + round_up(J * M, 8), 0);
+        len.resize(len.size() + round_up(J, 4), 0);
+        rem.resize(rem.size() + round_up(J * (M + 1), 8), 0);
+        for (int j = 0; j < J; j++) {
+            int64_t total = 0;
+            for (int i = 0; i < M; i++) {
+                const int m = mm[j * M + i], t = dd[j * M + i];
+                if (m < 0 || m >= M) return fail(h, JSS_ERR_INVALID, "instance %d: machine %d out of range", k, m);
+                // zero-length ops would put an event at the current time, which the
+                // queue-free time advance cannot represent
+                if (t < 1 || t > JSS_MAX_DURATION)
+                    return fail(h, JSS_ERR_UNSUPPORTED, "instance %d: duration %d outside [1, %d]", k, t,
+                                JSS_MAX_DURATION);
+                ops[d.ops_off + j * M + i] = (uint16_t)((m << JSS_OP_SHIFT) | t);
+                total += t;
+                hi.max_time_op = std::max<int64_t>(hi.max_time_op, t);  // jss_env.py:86
+            }
+            len[d.len_off + j] = (int32_t)total;                        // jss_env.py:87
+            hi.sum_op += total;                                         // jss_env.py:88
+            hi.max_time_jobs = std::max(hi.max_time_jobs, total);       // jss_env.py:89
+            int64_t suffix = 0;
+            rem[d.rem_off + j * (M + 1) + M] = 0;
+            for (int i = M - 1; i >= 0; i--) {
+                suffix += dd[j * M + i];
+                rem[d.rem_off + j * (M + 1) + i] = (uint16_t)suffix;    // <= 32 * 2047 < 65536
+            }
+        }
+        d.max_time_op = (int32_t)hi.max_time_op;
+        d.max_time_jobs = (int32_t)hi.max_time_jobs;
+        d.sum_op = (int32_t)hi.sum_op;
+        h->insts[k] = hi;
+        h->descs[k] = d;
+    }
+    int rc;
+    if ((rc = dev_alloc(h, &h->d_inst, (size_t)n_inst))) return rc;
+    if ((rc = dev_alloc(h, &h->d_ops, ops.size()))) return rc;
+    if ((rc = dev_alloc(h, &h->d_len, len.size()))) return rc;
+    if ((rc = dev_alloc(h, &h->d_rem, rem.size()))) return rc;
+    JSS_CUDA(h, cudaMemcpy(h->d_inst, h->descs.data(), sizeof(JssInstDesc) * n_inst, cudaMemcpyHostToDevice));
+    JSS_CUDA(h, cudaMemcpy(h->d_ops, ops.data(), ops.size() * 2, cudaMemcpyHostToDevice));
+    JSS_CUDA(h, cudaMemcpy(h->d_len, len.data(), len.size() * 4, cudaMemcpyHostToDevice));
+    JSS_CUDA(h, cudaMemcpy(h->d_rem, rem.data(), rem.size() * 2, cudaMemcpyHostToDevice));
+    h->loaded = true;
+    return JSS_OK;
+}
+
+int jss_instance_scalars(jss_t *h, int inst, int64_t out[3]) {
+    if (!h || !out || !h->loaded || inst < 0 || inst >= (int)h->insts.size())
+        return fail(h, JSS_ERR_INVALID, "jss_instance_scalars: bad arguments");
+    out[0] = h->insts[inst].max_time_op;
+    out[1] = h->insts[inst].max_time_jobs;
+    out[2] = h->insts[inst].sum_op;
+    return JSS_OK;
+}
+
+int jss_assign(jss_t *h, const int32_t *env_to_inst) {
+    if (!h || !env_to_inst) return fail(h, JSS_ERR_INVALID, "jss_assign: bad arguments");
+    if (!h->loaded) return fail(h, JSS_ERR_STATE, "jss_load_instances must be called first");
+    if (h->assigned) return fail(h, JSS_ERR_STATE, "envs already assigned");
+    JSS_CUDA(h, cudaSetDevice(h->device));
+    const int N = h->n_envs, n_inst = (int)h->insts.size();
+    int jmax = 0, mmax = 0, ops_max = 0, rem_max = 0;
+    h->env_inst.assign(env_to_inst, env_to_inst + N);
+    std::vector<char> used(n_inst, 0);
+    for (int e = 0; e < N; e++) {
+        const int k = env_to_inst[e];
+        if (k < 0 || k >= n_inst) return fail(h, JSS_ERR_INVALID, "env %d: instance %d out of range", e, k);
+        used[k] = 1;
+    }
+    for (int k = 0; k < n_inst; k++) {
+        if (!used[k]) continue;
+        jmax = std::max(jmax, h->insts[k].J);
+        mmax = std::max(mmax, h->insts[k].M);
+        ops_max = std::max(ops_max, h->insts[k].J * h->insts[k].M);
+        rem_max = std::max(rem_max, h->insts[k].J * (h->insts[k].M + 1));
+    }
+    // group envs by (KJ class, instance) -> tiles of <= JSS_WARPS_PER_CTA envs of one instance
+    std::vector<int32_t> order(N);
+    for (int e = 0; e < N; e++) order[e] = e;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        const int ka = env_to_inst[a], kb = env_to_inst[b];
+        const int ca = class_of(kj_of(h->insts[ka].J)), cb = class_of(kj_of(h->insts[kb].J));
+        if (ca != cb) return ca < cb;
+        return ka < kb;
+    });
+    std::vector<JssTile> tiles;
+    for (int c = 0; c < 3; c++) h->class_tile_begin[c] = h->class_tile_end[c] = 0;
+    int pos = 0;
+    int cur_class = -1;
+    while (pos < N) {
+        const int k = env_to_inst[order[pos]];
+        const int c = class_of(kj_of(h->insts[k].J));
+        int end = pos;
+        while (end < N && env_to_inst[order[end]] == k) end++;
+        if (c != cur_class) {
+            if (cur_class >= 0) h->class_tile_end[cur_class] = (int)tiles.size();
+            h->class_tile_begin[c] = (int)tiles.size();
+            cur_class = c;
+        }
+        for (int f = pos; f < end; f += JSS_WARPS_PER_CTA) {
+            JssTile t;
+            t.first = f;
+            t.inst_count = (k << 8) | std::min(JSS_WARPS_PER_CTA, end - f);
+            tiles.push_back(t);
+        }
+        pos = end;
+    }
+    if (cur_class >= 0) h->class_tile_end[cur_class] = (int)tiles.size();
+
+    JssParams &p = h->p;
+    p.n_envs = N;
+    p.jobs_max = jmax;
+    p.machines_max = mmax;
+    p.Jcap = round_up(jmax, 4);
+    p.Mcap = round_up(mmax, 4);
+    p.block_words = 5 * p.Jcap + p.Mcap + 12;
+    p.mask_stride = round_up(jmax + 1, 4);
+    p.create_flags = (int32_t)h->create_flags;
+    p.env_id_base = h->env_id_base;
+    p.inst = h->d_inst; p.ops_pool = h->d_ops; p.len_pool = h->d_len; p.rem_pool = h->d_rem;
+
+    h->sl_norem.ops_elems = round_up(ops_max, 8);
+    h->sl_norem.len_elems = round_up(jmax, 4);
+    h->sl_norem.rem_elems = 0;
+    h->sl_norem.scratch_words = 7 * p.Jcap;
+    h->sl_rem = h->sl_norem;
+    h->sl_rem.rem_elems = round_up(rem_max, 8);
+
+    int rc;
+    int32_t *d_order = nullptr;
+    JssTile *d_tiles = nullptr;
+    if ((rc = dev_alloc(h, &d_order, (size_t)N))) return rc;
+    if ((rc = dev_alloc(h, &d_tiles, tiles.size()))) return rc;
+    JSS_CUDA(h, cudaMemcpy(d_order, order.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
+    JSS_CUDA(h, cudaMemcpy(d_tiles, tiles.data(), tiles.size() * sizeof(JssTile), cudaMemcpyHostToDevice));
+    p.order = d_order;
+    p.tiles = d_tiles;
+    const size_t NJ = (size_t)N * jmax, NM = (size_t)N * mmax;
+    if ((rc = dev_alloc(h, &p.state, (size_t)N * p.block_words))) return rc;
+    if ((rc = dev_alloc(h, &p.mask, (size_t)N * p.mask_stride))) return rc;
+    if ((rc = dev_alloc(h, &p.obs, NJ * 7))) return rc;
+    if ((rc = dev_alloc(h, &p.reward, (size_t)N))) return rc;
+    if ((rc = dev_alloc(h, &p.reward_raw, (size_t)N))) return rc;
+    if ((rc = dev_alloc(h, &p.done, (size_t)N))) return rc;
+    if ((rc = dev_alloc(h, &p.time, (size_t)N))) return rc;
+    if ((rc = dev_alloc(h, &p.flags, (size_t)N))) return rc;
+    if (h->create_flags & JSS_CREATE_RECORD_SOLUTION) {
+        if ((rc = dev_alloc(h, &p.solution, NJ * mmax, false))) return rc;
+        JSS_CUDA(h, cudaMemset(p.solution, 0xff, NJ * mmax * 4));  // -1
+    } else {
+        p.solution = nullptr;
+    }
+    if ((rc = dev_alloc(h, &p.episode_count, (size_t)N))) return rc;
+    if ((rc = dev_alloc(h, &p.last_makespan, (size_t)N))) return rc;
+    if ((rc = dev_alloc(h, &p.last_return, (size_t)N))) return rc;
+    if ((rc = dev_alloc(h, &p.acc, (size_t)N * 4))) return rc;
+    if ((rc = dev_alloc(h, &p.x_todo, NJ))) return rc;
+    if ((rc = dev_alloc(h, &p.x_tufco, NJ))) return rc;
+    if ((rc = dev_alloc(h, &p.x_idle_last, NJ))) return rc;
+    if ((rc = dev_alloc(h, &p.x_total_idle, NJ))) return rc;
+    if ((rc = dev_alloc(h, &p.x_col4, NJ))) return rc;
+    if ((rc = dev_alloc(h, &p.x_tuam, NM))) return rc;
+    if ((rc = dev_alloc(h, &p.x_legal, NJ))) return rc;
+    if ((rc = dev_alloc(h, &p.x_blocked, NJ))) return rc;
+    if ((rc = dev_alloc(h, &h->d_stats, (size_t)JSS_STATS_LEN))) return rc;
+    if ((rc = dev_alloc(h, &h->dev_actions, (size_t)N))) return rc;
+    h->assigned = true;
+    // a fresh batch starts reset, like a freshly constructed + reset reference env
+    return jss_reset(h, nullptr, nullptr);
+}
+
+int jss_get_buffers(jss_t *h, jss_buffers *out) {
+    if (!h || !out) return JSS_ERR_INVALID;
+    if (!h->assigned) return fail(h, JSS_ERR_STATE, "jss_assign must be called first");
+    const JssParams &p = h->p;
+    memset(out, 0, sizeof *out);
+    out->n_envs = p.n_envs; out->jobs_max = p.jobs_max; out->machines_max = p.machines_max;
+    out->mask_stride = p.mask_stride;
+    out->action_mask = p.mask; out->real_obs = p.obs; out->reward = p.reward; out->reward_raw = p.reward_raw;
+    out->done = p.done; out->time = p.time; out->flags = p.flags; out->solution = p.solution;
+    out->episode_count = p.episode_count; out->last_makespan = p.last_makespan; out->last_return = p.last_return;
+    out->x_todo = p.x_todo; out->x_tufco = p.x_tufco; out->x_idle_last = p.x_idle_last;
+    out->x_total_idle = p.x_total_idle; out->x_col4 = p.x_col4; out->x_tuam = p.x_tuam;
+    out->x_legal = p.x_legal; out->x_blocked = p.x_blocked;
+    return JSS_OK;
+}
+
+int jss_reset(jss_t *h, const uint8_t *env_mask_dev, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    JssLaunch a{};
+    a.mode = JSS_MODE_RESET;
+    a.env_mask = env_mask_dev;
+    return launch_all(h, a, false, (cudaStream_t)stream);
+}
+
+int jss_step(jss_t *h, const int32_t *actions_dev, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!actions_dev) return fail(h, JSS_ERR_INVALID, "jss_step: actions_dev is NULL");
+    JssLaunch a{};
+    a.mode = JSS_MODE_STEP;
+    a.actions = actions_dev;
+    return launch_all(h, a, false, (cudaStream_t)stream);
+}
+
+int jss_policy(jss_t *h, int rule, int coin_mode, uint64_t seed, uint64_t step_index, int32_t *actions_dev,
+               void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!actions_dev || rule < 0 || rule >= JSS_NUM_RULES || (coin_mode != JSS_COIN_DEVICE && coin_mode != JSS_COIN_NEVER))
+        return fail(h, JSS_ERR_INVALID, "jss_policy: bad arguments (rule %d, coin %d)", rule, coin_mode);
+    JssLaunch a{};
+    a.mode = JSS_MODE_POLICY;
+    a.rule = rule; a.coin_mode = coin_mode; a.seed = seed; a.step_index = step_index;
+    a.actions_out = actions_dev;
+    return launch_all(h, a, rule_wants_rem(rule), (cudaStream_t)stream);
+}
+
+int jss_rollout(jss_t *h, int rule, uint64_t seed, uint64_t step_index, int n_steps, int write_obs, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (rule < 0 || rule >= JSS_NUM_RULES || n_steps < 0)
+        return fail(h, JSS_ERR_INVALID, "jss_rollout: bad arguments (rule %d, n_steps %d)", rule, n_steps);
+    JssLaunch a{};
+    a.mode = JSS_MODE_ROLLOUT;
+    a.rule = rule; a.coin_mode = JSS_COIN_DEVICE; a.seed = seed; a.step_index = step_index;
+    a.n_steps = n_steps; a.write_obs = write_obs;
+    return launch_all(h, a, rule_wants_rem(rule), (cudaStream_t)stream);
+}
+
+int jss_step_host(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, float *obs_host, float *reward_host,
+                  uint8_t *done_host, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!actions_host) return fail(h, JSS_ERR_INVALID, "jss_step_host: actions_host is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const JssParams &p = h->p;
+    const size_t N = (size_t)p.n_envs;
+    JSS_CUDA(h, cudaMemcpyAsync(h->dev_actions, actions_host, N * 4, cudaMemcpyHostToDevice, st));
+    rc = jss_step(h, h->dev_actions, stream);
+    if (rc) return rc;
+    if (mask_host)
+        JSS_CUDA(h, cudaMemcpy2DAsync(mask_host, (size_t)p.jobs_max + 1, p.mask, (size_t)p.mask_stride,
+                                      (size_t)p.jobs_max + 1, N, cudaMemcpyDeviceToHost, st));
+    if (obs_host)
+        JSS_CUDA(h, cudaMemcpyAsync(obs_host, p.obs, N * p.jobs_max * 7 * 4, cudaMemcpyDeviceToHost, st));
+    if (reward_host) JSS_CUDA(h, cudaMemcpyAsync(reward_host, p.reward, N * 4, cudaMemcpyDeviceToHost, st));
+    if (done_host) JSS_CUDA(h, cudaMemcpyAsync(done_host, p.done, N, cudaMemcpyDeviceToHost, st));
+    JSS_CUDA(h, cudaStreamSynchronize(st));
+    return JSS_OK;
+}
+
+int jss_stats(jss_t *h, int64_t *out_host, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!out_host) return fail(h, JSS_ERR_INVALID, "jss_stats: out_host is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long init[JSS_STATS_LEN] = {0, 0, 0, ~0ull, 0, 0, 0, 0};
+    JSS_CUDA(h, cudaMemcpyAsync(h->d_stats, init, sizeof init, cudaMemcpyHostToDevice, st));
+    const int threads = 256;
+    const int blocks = std::min((h->n_envs + threads - 1) / threads, h->sm_count * 4);
+    JSS_LAUNCH(jss_stats_kernel, blocks, threads, 0, st, h->p, h->d_stats);
+    JSS_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    unsigned long long res[JSS_STATS_LEN];
+    JSS_CUDA(h, cudaMemcpyAsync(res, h->d_stats, sizeof res, cudaMemcpyDeviceToHost, st));
+    JSS_CUDA(h, cudaStreamSynchronize(st));
+    for (int i = 0; i < JSS_STATS_LEN; i++) out_host[i] = (int64_t)res[i];
+    if (res[3] == ~0ull) out_host[3] = INT64_MAX;
+    return JSS_OK;
+}
+
+int jss_export_state(jss_t *h, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    JssLaunch a{};
+    a.mode = JSS_MODE_EXPORT;
+    return launch_all(h, a, false, (cudaStream_t)stream);
+}
+
+int jss_import_state(jss_t *h, const uint8_t *env_mask_dev, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    JssLaunch a{};
+    a.mode = JSS_MODE_IMPORT;
+    a.env_mask = env_mask_dev;
+    return launch_all(h, a, false, (cudaStream_t)stream);
+}
+
+int jss_host_masked_random(const uint8_t *mask_host, int n, int width, uint64_t seed, uint64_t env_id_base,
+                           uint64_t step_index, int32_t *actions_host) {
+    if (!mask_host || !actions_host || n < 0 || width <= 0) return JSS_ERR_INVALID;
+    auto work = [&](int lo, int hi) {
+        for (int e = lo; e < hi; e++) {
+            const uint8_t *row = mask_host + (size_t)e * width;
+            int cnt = 0;
+            for (int i = 0; i < width; i++) cnt += row[i] != 0;
+            int act = JSS_ACTION_SKIP;
+            if (cnt > 0) {
+                uint32_t r = jss_pick(jss_hash3(seed, env_id_base + (uint64_t)e, step_index), (uint32_t)cnt);
+                for (int i = 0; i < width; i++)
+                    if (row[i]) { if (r == 0) { act = i; break; } r--; }
+            }
+            actions_host[e] = act;
+        }
+    };
+    const int nthreads = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()),
+                                               std::max<size_t>(1, (size_t)n * width / (1 << 18)));
+    if (nthreads <= 1) { work(0, n); return JSS_OK; }
+    std::vector<std::thread> pool;
+    const int chunk = (n + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; t++) pool.emplace_back(work, std::min(n, t * chunk), std::min(n, (t + 1) * chunk));
+    for (auto &th : pool) th.join();
+    return JSS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// Host/device shared plain-data types of the batched job-shop kernels.
+#pragma once
+#include <stdint.h>
+
+// ---- packed instance tables (read-only, built by jss_load_instances) ----------
+// ops_pool  u16 [J*M]      op = (machine << 11) | duration   (M <= 32, duration <= 2047)
+// len_pool  i32 [J]        jobs_length[j] = sum of durations (jss_env.py:87)
+// rem_pool  u16 [J*(M+1)]  rem[j][k] = sum of durations of ops k..M-1 (rules MWR/LWR/CR)
+#define JSS_OP_SHIFT 11
+#define JSS_OP_DMASK 2047u
+#define JSS_OP_NONE 0xFFFFFFFFu  // register-only marker "job has no current op" (finished / padding): machine field >= 32
+
+struct JssInstDesc {
+    int32_t J, M;
+    int32_t max_time_op, max_time_jobs, sum_op;  // jss_env.py:86-89
+    int32_t ops_off;                              // offsets into the pools, in elements
+    int32_t len_off;
+    int32_t rem_off;
+};
+
+// ---- per-env state block in HBM (int32 words; every sub-array 16-byte aligned) ---
+//   [0      , Jcap )   todo_time_step_job            (padding slots hold M)
+//   [Jcap   , 2Jcap)   time_until_finish_current_op_jobs
+//   [2Jcap  , 3Jcap)   idle_time_jobs_last_op
+//   [3Jcap  , 4Jcap)   total_idle_time_jobs
+//   [4Jcap  , 5Jcap)   numerator of real_obs[:,4] (stale by design, jss_env.py:569-586)
+//   [5Jcap  , +Mcap)   time_until_available_machine
+//   then 4 words  legal ballots    L[i], bit l  <-> job KJ*l + i
+//        4 words  blocked ballots  B[i]  (action_illegal_no_op)
+//        4 words  header: current_time_step, flags, episode_steps, episode_return_raw
+// Not stored because derivable: event queue, illegal_actions
+// [M][J], machine_legal, both counters, needed_machine_jobs, total_perform_op_time_jobs.
+#define JSS_HDR_T 0
+#define JSS_HDR_FLAGS 1
+#define JSS_HDR_EP_STEPS 2
+#define JSS_HDR_EP_RETURN 3
+
+struct JssTile {       // one CTA work item: up to `count` envs of ONE instance
+    int32_t first;     // index into `order`
+    int32_t inst_count;  // (instance << 8) | count
+};
+
+struct JssParams {
+    int32_t n_envs, Jcap, Mcap, block_words;
+    int32_t jobs_max, machines_max, mask_stride, create_flags;
+    uint64_t env_id_base;
+    const JssInstDesc *inst;
+    const uint16_t *ops_pool;
+    const int32_t *len_pool;
+    const uint16_t *rem_pool;
+    const int32_t *order;    // env ids grouped by (KJ class, instance)
+    const JssTile *tiles;
+    int32_t *state;          // [N][block_words]
+    uint8_t *mask;           // [N][mask_stride]
+    float *obs;              // [N][jobs_max][7]
+    float *reward;
+    int32_t *reward_raw;
+    uint8_t *done;
+    int32_t *time;
+    uint32_t *flags;
+    int32_t *solution;       // [N][jobs_max][machines_max] or nullptr
+    int32_t *episode_count;
+    int32_t *last_makespan;
+    int32_t *last_return;
+    int64_t *acc;            // [N][4]: total finished-episode steps, sum makespan, sum return, (min<<32|max) packed
+    // canonical export buffers
+    int32_t *x_todo, *x_tufco, *x_idle_last, *x_total_idle, *x_col4, *x_tuam;
+    uint8_t *x_legal, *x_blocked;
+};
+
+struct JssLaunch {           // per-launch arguments
+    int32_t tile_begin, tile_end;
+    int32_t mode;            // JSS_MODE_*
+    int32_t rule, coin_mode, n_steps, write_obs;
+    uint64_t seed, step_index;
+    const int32_t *actions;  // step
+    int32_t *actions_out;    // policy
+    const uint8_t *env_mask; // reset / import
+};
+
+#define JSS_MODE_RESET 0
+#define JSS_MODE_STEP 1
+#define JSS_MODE_ROLLOUT 2
+#define JSS_MODE_POLICY 3
+#define JSS_MODE_EXPORT 4
+#define JSS_MODE_IMPORT 5
+
+#define JSS_WARPS_PER_CTA 8

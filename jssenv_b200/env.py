@@ -1,0 +1,171 @@
+"""JssEnv -- single-environment facade with the reference's object interface.
+
+Mirrors ``JSSEnv.envs.jss_env.JssEnv`` (JSSEnv/envs/jss_env.py:14-693): same ctor
+(``env_config={"instance_path": ...}``, default instance ta80), ``reset() -> obs``,
+``step(action) -> (obs, reward, done, False, {})``, ``get_legal_actions()``,
+``increase_time_step()`` and the attribute surface that the reference's dispatching
+rules and tests read (``todo_time_step_job``, ``machine_legal``, ``next_time_step``,
+``solution`` ...).  It is a batch of ONE env on the GPU: every transition runs the
+same sm_100a step kernel as ``JssVecEnv``; the attributes are host copies decoded
+from the device state after each transition (redundant reference state such as the
+event queue or ``illegal_actions[M][J]`` is re-derived).
+"""
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+from . import _native as N
+from .instances import DEFAULT_INSTANCE
+from .vec_env import JssVecEnv
+
+try:  # optional: only used to publish gym spaces / register the id
+    import gymnasium as _gym
+except Exception:  # gymnasium is not installed in the build image
+    _gym = None
+
+
+class _Space:
+    """Minimal stand-in for gym.spaces.* when gymnasium is absent."""
+
+    def __init__(self, kind, **kw):
+        self.kind = kind
+        self.__dict__.update(kw)
+
+    def __repr__(self):
+        return f"{self.kind}({ {k: v for k, v in self.__dict__.items() if k != 'kind'} })"
+
+
+class JssEnv(_gym.Env if _gym is not None else object):
+    def __init__(self, env_config: Optional[Dict[str, Any]] = None, device: int = 0):
+        if env_config is None:
+            env_config = {"instance_path": DEFAULT_INSTANCE}   # jss_env.py:35-38
+        self._vec = JssVecEnv(1, {"instance_path": env_config["instance_path"]}, device=device,
+                              record_solution=True)
+        machine, duration = self._vec.instances[0]
+        self.jobs, self.machines = int(machine.shape[0]), int(machine.shape[1])
+        self.instance_matrix = np.stack([machine, duration], axis=-1).astype(np.int64)   # (J, M, 2), jss_env.py:78
+        self.jobs_length = duration.sum(axis=1).astype(np.int64)
+        self.max_time_op, self.max_time_jobs, self.sum_op = (int(v) for v in self._vec.instance_scalars[0])
+        self.last_solution = None
+        self.last_time_step = float("inf")
+        J = self.jobs
+        if _gym is not None:
+            self.action_space = _gym.spaces.Discrete(J + 1)
+            self.observation_space = _gym.spaces.Dict({
+                "action_mask": _gym.spaces.Box(0, 1, shape=(J + 1,)),
+                "real_obs": _gym.spaces.Box(low=0.0, high=1.0, shape=(J, 7), dtype=float)})
+        else:
+            self.action_space = _Space("Discrete", n=J + 1)
+            self.observation_space = _Space("Dict", spaces={
+                "action_mask": _Space("Box", low=0, high=1, shape=(J + 1,)),
+                "real_obs": _Space("Box", low=0.0, high=1.0, shape=(J, 7), dtype=float)})
+        self._fresh = False
+        self._pull()
+
+    # ------------------------------------------------------------------ state mirror
+    def _pull(self):
+        """Copy the env's device state to the host and rebuild the reference's attributes."""
+        v = self._vec
+        x = v.export_state()
+        v.synchronize()
+        J, M = self.jobs, self.machines
+        g = lambda t: t[0].cpu().numpy()                      # noqa: E731
+        todo = g(x["todo"]).astype(np.int64)
+        tufco = g(x["tufco"]).astype(np.int64)
+        tuam = g(x["tuam"]).astype(np.int64)
+        self.todo_time_step_job = todo
+        self.time_until_finish_current_op_jobs = tufco
+        self.time_until_available_machine = tuam
+        self.idle_time_jobs_last_op = g(x["idle_last"]).astype(np.int64)
+        self.total_idle_time_jobs = g(x["total_idle"]).astype(np.int64)
+        self.action_illegal_no_op = g(x["blocked"]).astype(bool)
+        self.current_time_step = int(v.current_time_step[0])
+        flags = int(v.flags[0])
+        self._flags = flags
+        legal = np.zeros(J + 1, dtype=bool)
+        legal[:J] = g(x["legal"]).astype(bool)
+        legal[J] = bool(flags & N.FLAG_NOOP_LEGAL)
+        self.legal_actions = legal
+        unfinished = todo < M
+        safe = np.minimum(todo, M - 1)
+        ar = np.arange(J)
+        self.needed_machine_jobs = np.where(unfinished, self.instance_matrix[ar, safe, 0], -1).astype(np.int64)
+        cur_d = self.instance_matrix[ar, safe, 1]
+        # total_perform = t - total_idle until the job completes (then jobs_length)
+        self.total_perform_op_time_jobs = np.where(
+            unfinished, self.current_time_step - self.total_idle_time_jobs, self.jobs_length).astype(np.int64)
+        del cur_d
+        ml = np.zeros(M, dtype=bool)
+        ml[self.needed_machine_jobs[legal[:J]]] = True         # machine_legal == "some legal job needs it"
+        self.machine_legal = ml
+        self.nb_machine_legal = int(ml.sum())
+        self.nb_legal_actions = int(legal[:J].sum())
+        ia = np.zeros((M, J), dtype=bool)                      # illegal_actions[m][j] == blocked[j] & needed[j]==m
+        bj = np.flatnonzero(self.action_illegal_no_op)
+        ia[self.needed_machine_jobs[bj], bj] = True
+        self.illegal_actions = ia
+        # event queue == sorted set {t + tuam[m] : tuam[m] > 0} (appendix A.1)
+        self.next_time_step = sorted({int(self.current_time_step + d) for d in tuam if d > 0})
+        self.next_jobs = [int(np.flatnonzero((tufco > 0) & (self.current_time_step + tufco == e))[0])
+                          for e in self.next_time_step]
+        self.solution = v.solution[0].cpu().numpy().astype(np.int64)
+        self.state = v.real_obs[0].cpu().numpy().astype(np.float64)
+
+    def _get_current_state_representation(self):
+        return {"real_obs": self.state, "action_mask": self.legal_actions}
+
+    # ------------------------------------------------------------------ reference API
+    def get_legal_actions(self):
+        return self.legal_actions
+
+    def reset(self, *, seed=None, options=None):
+        """Returns the observation only, like the reference (jss_env.py:145-181)."""
+        self._vec.reset()
+        self._pull()
+        return self._get_current_state_representation()
+
+    def step(self, action: int):
+        a = int(action)
+        if not (0 <= a <= self.jobs):
+            raise IndexError(f"action {a} out of range")
+        self._vec.step(np.array([a], dtype=np.int32))
+        self._pull()
+        if self._flags & N.FLAG_ERROR:
+            # the reference raises IndexError here (jss_env.py:444 / :517) or silently corrupts
+            # its counters (illegal job action); the device env sets the sticky error bit
+            raise IndexError(f"illegal action {a} for the current state (error bit set)")
+        reward = float(self._vec.reward[0])
+        done = bool(self._vec.done[0])
+        if done:                                               # jss_env.py:649-652
+            self.last_time_step = self.current_time_step
+            self.last_solution = self.solution
+        return self._get_current_state_representation(), reward, done, False, {}
+
+    def increase_time_step(self) -> int:
+        """Raw time advance without the legal-action heuristics (jss_env.py:495-637)."""
+        self._vec.step(np.array([N.ACTION_ADVANCE], dtype=np.int32))
+        self._pull()
+        if self._flags & N.FLAG_ERROR:
+            raise IndexError("pop from empty list")           # what the reference raises (jss_env.py:517)
+        return -int(self._vec.reward_raw[0])
+
+    def rule_action(self, rule: str):
+        """(action, noop_legal) chosen on device by a dispatching rule, without the 10 % coin."""
+        a = self._vec.policy(rule, coin="never")
+        return int(a[0]), bool(self._flags & N.FLAG_NOOP_LEGAL)
+
+    def render(self, mode: str = "human"):
+        """Gantt rows of the current solution (jss_env.py:655-693 builds a plotly figure from the
+        same rows; plotting itself is out of scope here)."""
+        rows = []
+        for job in range(self.jobs):
+            for i in range(self.machines):
+                if self.solution[job][i] == -1:
+                    break
+                rows.append({"Task": f"Job {job}", "Start": int(self.solution[job][i]),
+                             "Finish": int(self.solution[job][i] + self.instance_matrix[job][i][1]),
+                             "Resource": f"Machine {int(self.instance_matrix[job][i][0])}"})
+        return rows or None
+
+    def close(self):
+        self._vec.close()

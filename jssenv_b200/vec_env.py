@@ -1,0 +1,230 @@
+"""JssVecEnv -- N independent job-shop environments stepped by the sm_100a kernels.
+
+Batched form of the reference's ``JssEnv`` contract (JSSEnv/envs/jss_env.py):
+``reset() -> obs`` (jss_env.py:145), ``step(actions) -> (obs, reward, done,
+truncated, info)`` (jss_env.py:403-481) with ``obs = {"real_obs": (N, J, 7) float32,
+"action_mask": (N, J+1) bool}`` (jss_env.py:112-119, 130-134).  As in the reference,
+the observation entries are LIVE ALIASES of the environment's buffers (here: device
+memory owned by the native library), the no-op is action index ``J``, actions are
+not validated beyond setting a per-env error bit, and ``truncated`` is always False.
+"""
+import ctypes
+from typing import Any, Dict, List, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _native as N
+from .instances import DEFAULT_INSTANCE, load_instance
+
+
+def _instance_list(env_config: Optional[Dict[str, Any]]):
+    """`env_config` keeps the reference key ``instance_path`` (jss_env.py:35-39) and adds
+    ``instance_paths`` (list) + ``env_to_instance`` (int array) for mixed batches."""
+    if env_config is None:
+        env_config = {"instance_path": DEFAULT_INSTANCE}
+    if "instance_paths" in env_config:
+        specs = list(env_config["instance_paths"])
+    else:
+        specs = [env_config["instance_path"]]
+    return [load_instance(s) for s in specs], env_config.get("env_to_instance")
+
+
+class JssVecEnv:
+    def __init__(self, num_envs: int, env_config: Optional[Dict[str, Any]] = None, device: int = 0,
+                 auto_reset: bool = False, record_solution: bool = False, env_id_base: int = 0, seed: int = 0):
+        self._h = ctypes.c_void_p()
+        self._L = N.backend.library()
+        self.num_envs = int(num_envs)
+        self.device_index = int(device)
+        self.seed = int(seed)
+        self.env_id_base = int(env_id_base)
+        self.auto_reset = bool(auto_reset)
+        self._step_index = 0
+        insts, env_to_inst = _instance_list(env_config)
+        self.instances = insts
+        flags = (N.CREATE_AUTO_RESET if auto_reset else 0) | (N.CREATE_RECORD_SOLUTION if record_solution else 0)
+        rc = self._L.jss_create(ctypes.byref(self._h), self.device_index, self.num_envs, flags, self.env_id_base)
+        N.check(None, rc, "jss_create")
+        # instance tables (jss_env.py:72-95)
+        jobs = np.array([m.shape[0] for m, _ in insts], np.int32)
+        machines = np.array([m.shape[1] for m, _ in insts], np.int32)
+        sizes = jobs.astype(np.int64) * machines
+        offsets = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+        mach = np.concatenate([m.reshape(-1) for m, _ in insts]).astype(np.int32)
+        dur = np.concatenate([d.reshape(-1) for _, d in insts]).astype(np.int32)
+        rc = self._L.jss_load_instances(self._h, len(insts), N.as_i32p(jobs), N.as_i32p(machines),
+                                        offsets.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                        N.as_i32p(mach), N.as_i32p(dur))
+        N.check(self._h, rc, "jss_load_instances")
+        if env_to_inst is None:
+            env_to_inst = np.arange(self.num_envs) % len(insts)
+        self.env_to_instance = np.ascontiguousarray(env_to_inst, dtype=np.int32)
+        assert self.env_to_instance.shape == (self.num_envs,)
+        rc = self._L.jss_assign(self._h, N.as_i32p(self.env_to_instance))   # also performs the first reset
+        N.check(self._h, rc, "jss_assign")
+        self.env_jobs = jobs[self.env_to_instance]           # J_i per env (no-op index of env i)
+        self.env_machines = machines[self.env_to_instance]
+        sc = np.zeros((len(insts), 3), np.int64)
+        for k in range(len(insts)):
+            N.check(self._h, self._L.jss_instance_scalars(
+                self._h, k, sc[k].ctypes.data_as(ctypes.POINTER(ctypes.c_int64))), "jss_instance_scalars")
+        self.instance_scalars = sc                           # max_time_op, max_time_jobs, sum_op
+        b = N.JssBuffers()
+        N.check(self._h, self._L.jss_get_buffers(self._h, ctypes.byref(b)), "jss_get_buffers")
+        self._b = b
+        self.jobs, self.machines = int(b.jobs_max), int(b.machines_max)
+        n, J, M, w = self.num_envs, self.jobs, self.machines, N.backend.wrap
+        d = self.device_index
+        self.device = N.backend.torch_device(d)
+        import torch
+        self._mask_u8 = w(b.action_mask, (n, J + 1), np.uint8, d, strides=(b.mask_stride, 1))
+        self.action_mask = self._mask_u8.view(torch.bool)
+        self.real_obs = w(b.real_obs, (n, J, 7), np.float32, d)
+        self.reward = w(b.reward, (n,), np.float32, d)
+        self.reward_raw = w(b.reward_raw, (n,), np.int32, d)
+        self.done = w(b.done, (n,), np.uint8, d).view(torch.bool)
+        self.current_time_step = w(b.time, (n,), np.int32, d)
+        self.flags = w(b.flags, (n,), np.int32, d)
+        self.solution = w(b.solution, (n, J, M), np.int32, d) if b.solution else None
+        self.episode_count = w(b.episode_count, (n,), np.int32, d)
+        self.last_makespan = w(b.last_makespan, (n,), np.int32, d)
+        self.last_return = w(b.last_return, (n,), np.int32, d)
+        self._x = {
+            "todo": w(b.x_todo, (n, J), np.int32, d), "tufco": w(b.x_tufco, (n, J), np.int32, d),
+            "idle_last": w(b.x_idle_last, (n, J), np.int32, d), "total_idle": w(b.x_total_idle, (n, J), np.int32, d),
+            "col4": w(b.x_col4, (n, J), np.int32, d), "tuam": w(b.x_tuam, (n, M), np.int32, d),
+            "legal": w(b.x_legal, (n, J), np.uint8, d), "blocked": w(b.x_blocked, (n, J), np.uint8, d),
+        }
+        self._truncated = torch.zeros(n, dtype=torch.bool, device=self.device)
+        self._actions = torch.zeros(n, dtype=torch.int32, device=self.device)
+
+    # ---------------------------------------------------------------- lifetime
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.jss_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return N.backend.stream(self.device_index)
+
+    def _obs(self):
+        return {"real_obs": self.real_obs, "action_mask": self.action_mask}
+
+    # ---------------------------------------------------------------- reference API, batched
+    def reset(self, mask=None):
+        """reset() of every env (or of the envs where `mask` is nonzero) -> obs (jss_env.py:145-181)."""
+        ptr = None
+        if mask is not None:
+            import torch
+            mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            ptr = ctypes.c_void_p(mask.data_ptr())
+        N.check(self._h, self._L.jss_reset(self._h, ptr, self._stream()), "jss_reset")
+        return self._obs()
+
+    def step(self, actions):
+        """actions: int32[N] on the env's device (torch) or anything torch.as_tensor accepts."""
+        import torch
+        a = torch.as_tensor(actions, device=self.device)
+        if a.dtype != torch.int32 or not a.is_contiguous():
+            a = a.to(torch.int32).contiguous()
+        N.check(self._h, self._L.jss_step(self._h, ctypes.c_void_p(a.data_ptr()), self._stream()), "jss_step")
+        return self._obs(), self.reward, self.done, self._truncated, {}
+
+    def get_legal_actions(self):
+        return self.action_mask
+
+    # ---------------------------------------------------------------- policies on device
+    def policy(self, rule: Union[str, int] = "RANDOM", coin: str = "device", out=None, step_index=None):
+        """Device-side action selection (masked-uniform sampler or a dispatching rule)."""
+        r = N.RULES[rule.upper()] if isinstance(rule, str) else int(rule)
+        out = self._actions if out is None else out
+        if step_index is None:
+            step_index = self._step_index
+            self._step_index += 1
+        rc = self._L.jss_policy(self._h, r, N.COIN_DEVICE if coin == "device" else N.COIN_NEVER, self.seed,
+                                int(step_index), ctypes.c_void_p(out.data_ptr()), self._stream())
+        N.check(self._h, rc, "jss_policy")
+        return out
+
+    def rollout(self, rule: Union[str, int], n_steps: int, write_obs: bool = True):
+        """n_steps x (policy -> step) fused on device (DispatchingRule.run_episode, dispatching.py:55-75)."""
+        r = N.RULES[rule.upper()] if isinstance(rule, str) else int(rule)
+        rc = self._L.jss_rollout(self._h, r, self.seed, self._step_index, int(n_steps), int(bool(write_obs)),
+                                 self._stream())
+        N.check(self._h, rc, "jss_rollout")
+        self._step_index += int(n_steps)
+        return self._obs(), self.reward, self.done, self._truncated, {}
+
+    # ---------------------------------------------------------------- host-buffer form
+    def step_host(self, actions: np.ndarray, want_obs: bool = True):
+        """step() with HOST buffers: H2D of the actions and D2H of the results inside the call."""
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        n, J = self.num_envs, self.jobs
+        if not hasattr(self, "_host"):
+            import torch
+            pin = N.backend.name == "cuda"
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin)   # noqa: E731
+            self._host = {"mask": mk((n, J + 1), torch.uint8), "obs": mk((n, J, 7), torch.float32),
+                          "reward": mk((n,), torch.float32), "done": mk((n,), torch.uint8)}
+        hb = self._host
+        rc = self._L.jss_step_host(self._h, ctypes.c_void_p(a.ctypes.data), ctypes.c_void_p(hb["mask"].data_ptr()),
+                                   ctypes.c_void_p(hb["obs"].data_ptr()) if want_obs else None,
+                                   ctypes.c_void_p(hb["reward"].data_ptr()), ctypes.c_void_p(hb["done"].data_ptr()),
+                                   self._stream())
+        N.check(self._h, rc, "jss_step_host")
+        obs = {"real_obs": hb["obs"].numpy(), "action_mask": hb["mask"].numpy().view(np.bool_)}
+        return obs, hb["reward"].numpy(), hb["done"].numpy().view(np.bool_), np.zeros(n, np.bool_), {}
+
+    def host_masked_random(self, mask: np.ndarray, step_index: int) -> np.ndarray:
+        """Same draw as policy('RANDOM') but from a host mask (for host-side agents / tests)."""
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        out = np.empty(m.shape[0], np.int32)
+        rc = self._L.jss_host_masked_random(ctypes.c_void_p(m.ctypes.data), m.shape[0], m.shape[1], self.seed,
+                                            self.env_id_base, int(step_index), ctypes.c_void_p(out.ctypes.data))
+        if rc != 0:
+            raise N.NativeError("jss_host_masked_random failed")
+        return out
+
+    # ---------------------------------------------------------------- statistics / state
+    def stats(self) -> Dict[str, int]:
+        out = np.zeros(len(N.STATS_KEYS), np.int64)
+        rc = self._L.jss_stats(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), self._stream())
+        N.check(self._h, rc, "jss_stats")
+        return dict(zip(N.STATS_KEYS, (int(v) for v in out)))
+
+    def export_state(self) -> Dict[str, Any]:
+        """Canonical per-env integer state as device tensors (snapshot); see jss_b200.h."""
+        N.check(self._h, self._L.jss_export_state(self._h, self._stream()), "jss_export_state")
+        d = dict(self._x)
+        d["t"] = self.current_time_step
+        d["flags"] = self.flags
+        return d
+
+    def import_state(self, state: Dict[str, Any], mask=None):
+        """Restore a snapshot taken with export_state() (tensors are copied into the library's buffers)."""
+        for k, dst in self._x.items():
+            if state[k].data_ptr() != dst.data_ptr():
+                dst.copy_(state[k])
+        if state["t"].data_ptr() != self.current_time_step.data_ptr():
+            self.current_time_step.copy_(state["t"])
+        if state["flags"].data_ptr() != self.flags.data_ptr():
+            self.flags.copy_(state["flags"])
+        ptr = None
+        if mask is not None:
+            import torch
+            mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            ptr = ctypes.c_void_p(mask.data_ptr())
+        N.check(self._h, self._L.jss_import_state(self._h, ptr, self._stream()), "jss_import_state")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.jss_launch_count(self._h))
+
+    def synchronize(self):
+        N.backend.synchronize(self.device_index)
