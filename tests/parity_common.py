@@ -1,0 +1,398 @@
+"""Backend-agnostic parity checks: the native env (real CUDA library in the `-m gpu`
+tests, host emulation of the same kernels in tests/test_emu_parity.py) against the CPU
+oracle and the golden fixtures recorded from the unmodified Python reference.
+
+Bars: bit-exact action_mask / done / current_time_step / raw
+integer reward / integer state; |real_obs - ref| <= 1e-6 and scaled reward within
+max(1e-6, 1.2e-7 * |r|) (fp32 device vs fp64 reference).
+"""
+import numpy as np
+
+from jssenv_b200 import JssEnv, JssVecEnv
+from jssenv_b200 import _native as N
+from jssenv_b200.dispatching import DISPATCHING_RULES, get_rule
+from jssenv_b200.instances import load_instance
+from oracle.jss_oracle import OracleEnv, OracleError
+from tests.helpers import load_json, load_trace, replay_optimal
+
+OBS_TOL = 1e-6
+
+
+def _np(t):
+    return t.cpu().numpy() if hasattr(t, "cpu") else np.asarray(t)
+
+
+def rew_close(a, b):
+    return abs(float(a) - float(b)) <= max(1e-6, 1.2e-7 * abs(float(b)))
+
+
+def compare_env_to_oracle(env, i, o, obs, reward=None, done=None, raw=None, ctx=""):
+    J = o.jobs
+    mask = _np(obs["action_mask"][i])
+    assert np.array_equal(mask[: J + 1], o.legal_actions), f"{ctx}: mask env {i}"
+    assert not mask[J + 1:].any(), f"{ctx}: padding mask bytes must stay 0"
+    ro = _np(obs["real_obs"][i])
+    assert np.abs(ro[:J] - o.state).max() <= OBS_TOL, f"{ctx}: real_obs env {i}"
+    assert ro.min() >= 0.0 and ro.max() <= 1.0
+    assert int(env.current_time_step[i]) == o.current_time_step, f"{ctx}: time env {i}"
+    if reward is not None:
+        assert rew_close(reward[0], reward[1]), f"{ctx}: reward {reward}"
+    if raw is not None:
+        assert int(raw[0]) == int(raw[1]), f"{ctx}: raw reward {raw}"
+    if done is not None:
+        assert bool(done[0]) == bool(done[1]), f"{ctx}: done"
+
+
+def compare_exported_state(env, oracles, alive=None, ctx=""):
+    """Every integer array of the reference, including the derived ones."""
+    x = {k: _np(v) for k, v in env.export_state().items()}
+    env.synchronize()
+    for i, o in enumerate(oracles):
+        if alive is not None and not alive[i]:
+            continue
+        J, M = o.jobs, o.machines
+        assert np.array_equal(x["todo"][i, :J], o.todo_time_step_job), f"{ctx} todo {i}"
+        assert np.array_equal(x["tufco"][i, :J], o.time_until_finish_current_op_jobs), f"{ctx} tufco {i}"
+        assert np.array_equal(x["idle_last"][i, :J], o.idle_time_jobs_last_op), f"{ctx} idle_last {i}"
+        assert np.array_equal(x["total_idle"][i, :J], o.total_idle_time_jobs), f"{ctx} total_idle {i}"
+        assert np.array_equal(x["tuam"][i, :M], o.time_until_available_machine), f"{ctx} tuam {i}"
+        assert np.array_equal(x["legal"][i, :J].astype(bool), o.legal_actions[:J]), f"{ctx} legal {i}"
+        assert np.array_equal(x["blocked"][i, :J].astype(bool), o.action_illegal_no_op), f"{ctx} blocked {i}"
+        assert int(x["t"][i]) == o.current_time_step
+        # stale column 4 numerator (appendix A.3)
+        col4 = x["col4"][i, :J].astype(np.float64) / o.max_time_op
+        assert np.abs(col4 - o.state[:, 4]).max() <= 1e-12, f"{ctx} col4 {i}"
+
+
+def check_random_batch(make_env, names, n_steps, seed, state_every=25, noop_force_every=0):
+    """Mixed batch; the ORACLE side picks masked-random actions (optionally a forced no-op
+    whenever an event is pending, like tests/test_solutions.py:762), both sides step."""
+    uniq = sorted(set(names))
+    env = make_env(len(names), {"instance_paths": uniq, "env_to_instance": [uniq.index(n) for n in names]})
+    oracles = [OracleEnv(*load_instance(n)) for n in names]
+    rng = np.random.default_rng(seed)
+    obs = env.reset()
+    for o in oracles:
+        o.reset()
+    for i, o in enumerate(oracles):
+        compare_env_to_oracle(env, i, o, obs, ctx="reset")
+    alive = np.ones(len(names), bool)
+    for step in range(n_steps):
+        acts = np.full(len(names), N.ACTION_SKIP, np.int32)
+        for i, o in enumerate(oracles):
+            if not alive[i]:
+                continue
+            legal = np.flatnonzero(o.legal_actions)
+            if noop_force_every and step % noop_force_every == noop_force_every - 1 and len(o.next_time_step) > 0:
+                acts[i] = o.jobs
+            else:
+                acts[i] = int(legal[rng.integers(len(legal))])
+        obs, reward, done, trunc, info = env.step(acts)
+        reward, done, raw = _np(reward), _np(done), _np(env.reward_raw)
+        assert not _np(trunc).any() and info == {}
+        for i, o in enumerate(oracles):
+            if not alive[i]:
+                continue
+            try:
+                oo, r, d, _, _ = o.step(int(acts[i]))
+            except OracleError:
+                # forced no-op that empties the event queue: the reference raises, the device flags it
+                assert int(env.flags[i]) & N.FLAG_ERROR, f"step {step} env {i}: expected error bit"
+                alive[i] = False
+                continue
+            assert not (int(env.flags[i]) & N.FLAG_ERROR), f"step {step} env {i}: unexpected error bit"
+            compare_env_to_oracle(env, i, o, obs, (reward[i], r), (done[i], d), (raw[i], o.last_raw_reward),
+                                  ctx=f"step {step} action {acts[i]}")
+            if d:
+                alive[i] = False
+                assert int(env.last_makespan[i]) == o.current_time_step
+        if step % state_every == 0:
+            compare_exported_state(env, oracles, alive, ctx=f"step {step}")
+        if not alive.any():
+            break
+    return env, oracles
+
+
+def check_golden_trace(make_env, path):
+    """Replay a trace recorded from the unmodified Python reference (tests/golden)."""
+    tr = load_trace(path)
+    env = make_env(1, {"instance_path": tr["inst"]})
+    obs = env.reset()
+    J = tr["mask"].shape[1] - 1
+
+    def check(k):
+        assert np.array_equal(_np(obs["action_mask"][0])[: J + 1], tr["mask"][k]), f"mask {k}"
+        assert np.abs(_np(obs["real_obs"][0])[:J] - tr["obs"][k]).max() <= OBS_TOL, f"obs {k}"
+        assert int(env.current_time_step[0]) == tr["t"][k]
+
+    check(0)
+    for k, a in enumerate(tr["actions"]):
+        obs, reward, done, _, _ = env.step(np.array([a], np.int32))
+        assert rew_close(reward[0], tr["reward"][k]), f"reward {k}"
+        assert bool(done[0]) == bool(tr["done"][k])
+        check(k + 1)
+        if k % 50 == 0:
+            x = {n: _np(v) for n, v in env.export_state().items()}
+            assert np.array_equal(x["todo"][0, :J], tr["todo"][k + 1])
+            assert np.array_equal(x["blocked"][0, :J].astype(bool), tr["blocked"][k + 1])
+            assert np.array_equal(x["tuam"][0, : tr["tuam"].shape[1]], tr["tuam"][k + 1])
+
+
+def check_facade_optimal(inst):
+    """The reference's known-answer replays (tests/test_solutions.py) through the JssEnv facade,
+    including its attribute surface (machine_legal, needed_machine_jobs, next_time_step ...)."""
+    spec = load_json("optimal_sequences.json")[inst]
+    env = JssEnv({"instance_path": inst})
+    assert replay_optimal(env, spec) == spec["makespan"]
+    assert env.last_time_step == spec["makespan"]
+    assert env.solution.min() != -1 and (env.todo_time_step_job == env.machines).all()
+    assert len(env.next_time_step) == 0
+    env.reset()
+    assert env.current_time_step == 0
+    env.close()
+
+
+def check_facade_attributes(inst, n_steps, seed):
+    """Every attribute the reference exposes, against the oracle, along a random trace."""
+    env = JssEnv({"instance_path": inst})
+    o = OracleEnv(*load_instance(inst))
+    rng = np.random.default_rng(seed)
+    obs, _ = env.reset(), o.reset()
+    assert env.jobs == o.jobs and env.machines == o.machines
+    assert (env.max_time_op, env.max_time_jobs, env.sum_op) == (o.max_time_op, o.max_time_jobs, o.sum_op)
+    assert np.array_equal(env.instance_matrix, o.instance_matrix)
+    done = False
+    for _ in range(n_steps):
+        for name in ("legal_actions", "machine_legal", "needed_machine_jobs", "todo_time_step_job",
+                     "time_until_available_machine", "time_until_finish_current_op_jobs",
+                     "total_perform_op_time_jobs", "total_idle_time_jobs", "idle_time_jobs_last_op",
+                     "action_illegal_no_op", "illegal_actions", "solution"):
+            assert np.array_equal(getattr(env, name), getattr(o, name)), name
+        assert env.nb_legal_actions == o.nb_legal_actions and env.nb_machine_legal == o.nb_machine_legal
+        assert env.next_time_step == o.next_time_step
+        assert env.current_time_step == o.current_time_step
+        assert obs["real_obs"].dtype == np.float64 and obs["real_obs"].shape == (o.jobs, 7)
+        assert np.abs(env.state - o.state).max() <= OBS_TOL
+        if done:
+            break
+        legal = np.flatnonzero(o.legal_actions)
+        a = int(legal[rng.integers(len(legal))])
+        obs, r, done, trunc, info = env.step(a)
+        _, r2, d2, _, _ = o.step(a)
+        assert rew_close(r, r2) and done == d2 and trunc is False and info == {}
+    env.close()
+
+
+def check_rules_seeded(inst):
+    """Rule episodes with np.random.seed(0) reproduce the reference's makespans (dispatching.py)."""
+    gold = load_json("rule_makespans.json")[inst]
+    env = JssEnv({"instance_path": inst})
+    for name, rule in DISPATCHING_RULES.items():
+        np.random.seed(0)
+        total, makespan = rule.run_episode(env)
+        assert makespan == gold[name]["makespan"], (inst, name)
+        assert abs(total - gold[name]["total_reward"]) <= 1e-3, (inst, name)
+    try:
+        get_rule("NOPE")
+        raise AssertionError("get_rule must raise ValueError")   # tests/test_dispatching.py:39-47
+    except ValueError:
+        pass
+    env.close()
+
+
+def check_policy_kernels(make_env, names, n_steps, seed):
+    """jss_policy for every rule vs the oracle's rule functions on identical states, with the
+    coin uniform taken from the shared counter RNG; RANDOM vs the oracle's sampler and the
+    host helper jss_host_masked_random."""
+    uniq = sorted(set(names))
+    env = make_env(len(names), {"instance_paths": uniq, "env_to_instance": [uniq.index(n) for n in names]}, seed=seed)
+    oracles = [OracleEnv(*load_instance(n)) for n in names]
+    obs = env.reset()
+    for o in oracles:
+        o.reset()
+    rules = ["SPT", "FIFO", "MWR", "LWR", "MOR", "LOR", "CR"]
+    alive = np.ones(len(names), bool)
+    for step in range(n_steps):
+        # every rule on the CURRENT state (explicit step_index so all rules see the same coin)
+        for rule in rules:
+            a_dev = _np(env.policy(rule, coin="device", step_index=step)).copy()
+            a_never = _np(env.policy(rule, coin="never", step_index=step)).copy()
+            for i, o in enumerate(oracles):
+                if not alive[i]:
+                    continue
+                u = _coin_uniform(env.seed, env.env_id_base + i, step)
+                exp, consumed = o.rule_action(rule, u)
+                assert a_dev[i] == exp, (step, rule, i, a_dev[i], exp)
+                exp_never, _ = o.rule_action(rule, 1.0)
+                assert a_never[i] == exp_never, (step, rule, i)
+        a = _np(env.policy("RANDOM", step_index=step)).copy()
+        host = env.host_masked_random(np.ascontiguousarray(_np(env.action_mask)), step)
+        for i, o in enumerate(oracles):
+            if alive[i]:
+                assert a[i] == o.masked_random_action(env.seed, env.env_id_base + i, step), (step, i)
+                assert a[i] == host[i]
+            else:
+                a[i] = N.ACTION_SKIP
+        obs, _, done, _, _ = env.step(a)
+        for i, o in enumerate(oracles):
+            if alive[i]:
+                _, _, d, _, _ = o.step(int(a[i]))
+                compare_env_to_oracle(env, i, o, obs, ctx=f"policy step {step}")
+                alive[i] = not d
+        if not alive.any():
+            break
+
+
+def _coin_uniform(seed, env, ctr):
+    """u = hash3(seed, env, ctr) / 2^32 -- jssenv_b200/csrc/jss_rng.h restated for the test."""
+    M = (1 << 64) - 1
+    z = (seed + 0x9E3779B97F4A7C15 * (env + 1) + 0xD1B54A32D192ED03 * (ctr + 1)) & M
+    z ^= z >> 30; z = (z * 0xBF58476D1CE4E5B9) & M
+    z ^= z >> 27; z = (z * 0x94D049BB133111EB) & M
+    z ^= z >> 31
+    return (z >> 32) / 4294967296.0
+
+
+def check_rollout_matches_steps(make_env, names, rule, n_steps, seed):
+    """The fused rollout kernel == policy kernel + step kernel, transition for transition;
+    and both == the oracle driven by the same counter RNG."""
+    uniq = sorted(set(names))
+    cfg = {"instance_paths": uniq, "env_to_instance": [uniq.index(n) for n in names]}
+    a_env = make_env(len(names), cfg, seed=seed, auto_reset=True)
+    b_env = make_env(len(names), cfg, seed=seed, auto_reset=True)
+    a_env.reset(); b_env.reset()
+    a_env.rollout(rule, n_steps, write_obs=True)
+    for _ in range(n_steps):
+        b_env.step(b_env.policy(rule))
+    for name in ("action_mask", "real_obs", "reward", "reward_raw", "done", "current_time_step", "flags",
+                 "episode_count", "last_makespan", "last_return"):
+        assert np.array_equal(_np(getattr(a_env, name)), _np(getattr(b_env, name))), name
+    xa, xb = a_env.export_state(), b_env.export_state()
+    for k in xa:
+        assert np.array_equal(_np(xa[k]), _np(xb[k])), k
+    assert a_env.stats() == b_env.stats()
+    # oracle with the same RNG (auto-reset: a done env is reset by the next transition)
+    for i, n in enumerate(names):
+        o = OracleEnv(*load_instance(n))
+        o.reset()
+        done, episodes, makespan = False, 0, -1
+        for step in range(n_steps):
+            if done:
+                o.reset(); done = False
+                continue
+            if rule == "RANDOM":
+                a = o.masked_random_action(seed, i, step)
+            else:
+                a, _ = o.rule_action(rule, _coin_uniform(seed, i, step))
+            _, _, done, _, _ = o.step(a)
+            if done:
+                episodes += 1; makespan = o.current_time_step
+        assert int(a_env.episode_count[i]) == episodes, (i, n)
+        if episodes:
+            assert int(a_env.last_makespan[i]) == makespan
+        assert int(a_env.current_time_step[i]) == o.current_time_step
+        J = o.jobs
+        if not done:
+            assert np.array_equal(_np(a_env.action_mask[i])[: J + 1], o.legal_actions)
+            assert np.abs(_np(a_env.real_obs[i])[:J] - o.state).max() <= OBS_TOL
+    return a_env
+
+
+def check_errors_and_freeze(make_env):
+    """Reference exceptions -> sticky error bit, env unchanged; done envs freeze; masked reset."""
+    env = make_env(4, {"instance_path": "ta01"})
+    o = OracleEnv(*load_instance("ta01"))
+    obs = env.reset(); o.reset()
+    before = {k: _np(v).copy() for k, v in env.export_state().items()}
+    mask0, obs0 = _np(env.action_mask).copy(), _np(env.real_obs).copy()
+    # env0: no-op with empty queue (IndexError jss_env.py:517); env1: out of range; env2: skip; env3: legal
+    env.step(np.array([env.jobs, 99, N.ACTION_SKIP, 3], np.int32))
+    flags = _np(env.flags)
+    assert flags[0] & N.FLAG_ERROR and flags[1] & N.FLAG_ERROR and not flags[2] & N.FLAG_ERROR and not flags[3] & N.FLAG_ERROR
+    after = {k: _np(v).copy() for k, v in env.export_state().items()}
+    for k in before:
+        if k == "flags":
+            continue
+        assert np.array_equal(before[k][:3], after[k][:3]), k
+    assert np.array_equal(_np(env.action_mask)[:3], mask0[:3]) and np.array_equal(_np(env.real_obs)[:3], obs0[:3])
+    o.step(3)
+    compare_env_to_oracle(env, 3, o, env._obs(), ctx="legal env next to erroring envs")
+    # illegal job action: job 3 is now running -> not legal
+    env.step(np.array([N.ACTION_SKIP] * 3 + [3], np.int32))
+    assert _np(env.flags)[3] & N.FLAG_ERROR
+    compare_env_to_oracle(env, 3, o, env._obs(), ctx="illegal action leaves the env unchanged")
+    # masked reset clears only env 0 and 3
+    env.reset(np.array([1, 0, 0, 1], np.uint8))
+    flags = _np(env.flags)
+    assert flags[0] == 0 and flags[3] == 0 and flags[1] & N.FLAG_ERROR
+    assert int(env.current_time_step[3]) == 0 and _np(env.action_mask)[3, : env.jobs].all()
+    return env
+
+
+def check_auto_reset_and_stats(make_env, name, seed):
+    env = make_env(6, {"instance_path": name}, seed=seed, auto_reset=True)
+    o = OracleEnv(*load_instance(name))
+    env.reset()
+    n_steps = 2 * (2 * env.jobs * env.machines) + 10
+    ep_o, mk_o, ret_o, steps_o = [], [], [], 0
+    for i in range(1):
+        o.reset(); done = False; ret = 0
+        for step in range(n_steps):
+            if done:
+                o.reset(); done = False; ret = 0
+                continue
+            a = o.masked_random_action(seed, 0, step)
+            _, _, done, _, _ = o.step(a)
+            ret += o.last_raw_reward; steps_o += 1
+            if done:
+                mk_o.append(o.current_time_step); ret_o.append(ret)
+    for _ in range(n_steps):
+        env.step(env.policy("RANDOM"))
+    st = env.stats()
+    assert int(env.episode_count[0]) == len(mk_o) and int(env.last_makespan[0]) == mk_o[-1]
+    assert int(env.last_return[0]) == ret_o[-1]
+    # identity: raw episode return = 2*sum_op - M*makespan
+    assert ret_o[-1] == 2 * o.sum_op - o.machines * mk_o[-1]
+    assert st["episodes"] == int(_np(env.episode_count).sum()) and st["episodes"] >= 6
+    assert st["min_makespan"] <= st["max_makespan"] and st["envs_error"] == 0
+    lm = _np(env.last_makespan)
+    assert st["min_makespan"] <= lm.min() and st["max_makespan"] >= lm.max()
+    return env
+
+
+def check_snapshot_restore(make_env, name, seed):
+    env = make_env(3, {"instance_path": name}, seed=seed)
+    env.reset()
+    for _ in range(40):
+        env.step(env.policy("RANDOM"))
+    snap = {k: v.clone() for k, v in env.export_state().items()}
+    mask, obs = _np(env.action_mask).copy(), _np(env.real_obs).copy()
+    hist = []
+    for k in range(30):
+        a = env.policy("RANDOM", step_index=1000 + k).clone()
+        env.step(a)
+        hist.append((_np(a).copy(), _np(env.action_mask).copy(), _np(env.reward_raw).copy()))
+    env.import_state(snap)
+    assert np.array_equal(_np(env.action_mask), mask) and np.array_equal(_np(env.real_obs), obs)
+    for k in range(30):
+        a = env.policy("RANDOM", step_index=1000 + k)
+        assert np.array_equal(_np(a), hist[k][0])
+        env.step(a)
+        assert np.array_equal(_np(env.action_mask), hist[k][1]) and np.array_equal(_np(env.reward_raw), hist[k][2])
+    return env
+
+
+def check_step_host(make_env, name, seed):
+    env = make_env(5, {"instance_path": name}, seed=seed)
+    ref = make_env(5, {"instance_path": name}, seed=seed)
+    env.reset(); ref.reset()
+    mask = np.ascontiguousarray(_np(env.action_mask))
+    for k in range(60):
+        a = env.host_masked_random(mask, k)
+        obs, rew, done, trunc, _ = env.step_host(a)
+        ref.step(a)
+        assert np.array_equal(obs["action_mask"], _np(ref.action_mask))
+        assert np.array_equal(obs["real_obs"], _np(ref.real_obs))
+        assert np.array_equal(rew, _np(ref.reward)) and np.array_equal(done, _np(ref.done))
+        mask = obs["action_mask"]
+    return env

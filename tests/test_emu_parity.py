@@ -1,0 +1,82 @@
+"""Kernel logic + Python host layer under HOST EMULATION of the CUDA kernels (tests/emu):
+the same jss_device.cuh / jss_api.cu compiled with g++, 32 fibers per warp, strict
+collectives.  Pre-GPU safety net only -- the authoritative parity tests are the
+`-m gpu` ones in tests/test_gpu_parity.py, which run the real sm_100a library.
+Sizes are kept small so the CPU suite stays fast."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import parity_common as pc
+from tests.emu.emu_backend import use_emulation
+from tests.helpers import GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _emu():
+    with use_emulation():
+        yield
+
+
+def make_env(n, cfg, **kw):
+    from jssenv_b200 import JssVecEnv
+    return JssVecEnv(n, cfg, **kw)
+
+
+def test_emu_random_mixed_batch_all_lane_classes():
+    # KJ=1 (15, 20, 30 jobs), KJ=2 (50 jobs), KJ=4 (100 jobs), Demirkol (durations to 200)
+    names = ["ta01", "ta01", "ta11", "ta21", "ta31", "ta41", "dmu16", "ta51", "ta61", "ta71", "ta80"]
+    pc.check_random_batch(make_env, names, n_steps=400, seed=11)
+
+
+def test_emu_full_episode_ta80():
+    pc.check_random_batch(make_env, ["ta80"], n_steps=3000, seed=5, state_every=100)
+
+
+def test_emu_forced_noops():
+    pc.check_random_batch(make_env, ["ta01", "ta45", "ta62", "ta80"], n_steps=500, seed=3, noop_force_every=5)
+
+
+@pytest.mark.parametrize("name", ["trace_ta01_random0", "trace_ta01_forcednoop3", "trace_ta41_lowest0",
+                                  "trace_dmu16_random7", "trace_ta80_highest0"])
+def test_emu_golden_reference_trace(name):
+    pc.check_golden_trace(make_env, os.path.join(GOLDEN, name + ".npz"))
+
+
+@pytest.mark.parametrize("inst", ["ta01", "ta41", "ta51"])
+def test_emu_facade_optimal_makespan(inst):
+    pc.check_facade_optimal(inst)
+
+
+def test_emu_facade_attributes():
+    pc.check_facade_attributes("ta01", 400, seed=2)
+
+
+def test_emu_rules_seeded_ta01():
+    pc.check_rules_seeded("ta01")
+
+
+def test_emu_policy_kernels():
+    pc.check_policy_kernels(make_env, ["ta01", "ta31", "ta51", "ta80"], n_steps=150, seed=9)
+
+
+@pytest.mark.parametrize("rule", ["RANDOM", "FIFO", "MWR", "CR"])
+def test_emu_rollout_matches_steps(rule):
+    pc.check_rollout_matches_steps(make_env, ["ta01", "ta01", "ta51", "ta80"], rule, n_steps=330, seed=4)
+
+
+def test_emu_errors_freeze_reset():
+    pc.check_errors_and_freeze(make_env)
+
+
+def test_emu_auto_reset_and_stats():
+    pc.check_auto_reset_and_stats(make_env, "ta01", seed=6)
+
+
+def test_emu_snapshot_restore():
+    pc.check_snapshot_restore(make_env, "ta31", seed=8)
+
+
+def test_emu_step_host():
+    pc.check_step_host(make_env, "ta01", seed=1)
