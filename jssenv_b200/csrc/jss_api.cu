@@ -102,20 +102,30 @@ size_t smem_bytes(const JssSmemLayout &sl) {
            (size_t)JSS_WARPS_PER_CTA * sl.scratch_words * 4;
 }
 
-template <int KJ>
-int launch_class(jss_t *h, const JssLaunch &a, const JssSmemLayout &sl, cudaStream_t st) {
+template <int KJ, int MODE>
+int launch_variant(jss_t *h, const JssLaunch &a, const JssSmemLayout &sl, cudaStream_t st) {
     const int n_tiles = a.tile_end - a.tile_begin;
-    if (n_tiles <= 0) return JSS_OK;
     const size_t smem = smem_bytes(sl);
+    auto kern = jss_env_kernel<KJ, MODE>;
     int per_sm = 0;
-    JSS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jss_env_kernel<KJ>,
-                                                               JSS_WARPS_PER_CTA * 32, smem));
+    JSS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, JSS_WARPS_PER_CTA * 32, smem));
     if (per_sm < 1) return fail(h, JSS_ERR_CUDA, "kernel does not fit on an SM (smem %zu B)", smem);
     const int grid = std::min(n_tiles, h->sm_count * per_sm);
-    JSS_LAUNCH(jss_env_kernel<KJ>, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl);
+    JSS_LAUNCH(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl);
     JSS_CUDA(h, cudaGetLastError());
     h->launches += 1;
     return JSS_OK;
+}
+
+template <int KJ>
+int launch_class(jss_t *h, const JssLaunch &a, const JssSmemLayout &sl, cudaStream_t st) {
+    if (a.tile_end - a.tile_begin <= 0) return JSS_OK;
+    switch (a.mode) {
+    case JSS_MODE_STEP: return launch_variant<KJ, JSS_MODE_STEP>(h, a, sl, st);
+    case JSS_MODE_POLICY: return launch_variant<KJ, JSS_MODE_POLICY>(h, a, sl, st);
+    case JSS_MODE_ROLLOUT: return launch_variant<KJ, JSS_MODE_ROLLOUT>(h, a, sl, st);
+    default: return launch_variant<KJ, JSS_MODE_RESET>(h, a, sl, st);   // reset / export / import
+    }
 }
 
 int launch_all(jss_t *h, JssLaunch a, bool want_rem, cudaStream_t st) {

@@ -145,6 +145,36 @@ JSS_DEV void env_load(const JssParams &p, const InstView &iv, int env, int lane,
     env_derive_ops<KJ>(iv, s, lane);
 }
 
+// policy kernels read only what the rule looks at: the ballots + header always, todo for
+// every rule (current op / remaining work / remaining ops), idle_last for FIFO
+template <int KJ>
+JSS_DEV void env_load_for_policy(const JssParams &p, const InstView &iv, int env, int lane, EnvRegs<KJ> &s,
+                                 int rule) {
+    const int32_t *blk = p.state + (size_t)env * p.block_words;
+    const int Jc = p.Jcap;
+#pragma unroll
+    for (int i = 0; i < KJ; i++) { s.todo[i] = iv.M; s.tufco[i] = 0; s.idle_last[i] = 0; s.total_idle[i] = 0; s.col4[i] = 0; }
+    if (rule != JSS_RULE_RANDOM && KJ * lane < Jc) {
+        jss_ld<KJ>(blk + KJ * lane, s.todo);
+        if (rule == JSS_RULE_FIFO) jss_ld<KJ>(blk + 2 * Jc + KJ * lane, s.idle_last);
+    }
+#pragma unroll
+    for (int i = 0; i < KJ; i++)
+        if (KJ * lane + i >= iv.J) { s.todo[i] = iv.M; s.idle_last[i] = 0; }
+    s.tuam = 0;
+    const int4 *tail = reinterpret_cast<const int4 *>(blk + 5 * Jc + p.Mcap);
+    int4 l4 = tail[0], h4 = tail[2];
+    const uint32_t lw[4] = {(uint32_t)l4.x, (uint32_t)l4.y, (uint32_t)l4.z, (uint32_t)l4.w};
+#pragma unroll
+    for (int i = 0; i < KJ; i++) { s.L[i] = lw[i]; s.B[i] = 0u; }
+    s.t = h4.x; s.flags = (uint32_t)h4.y; s.ep_steps = h4.z; s.ep_return = h4.w;
+    if (rule != JSS_RULE_RANDOM) env_derive_ops<KJ>(iv, s, lane);
+    else {
+#pragma unroll
+        for (int i = 0; i < KJ; i++) s.op[i] = JSS_OP_NONE;
+    }
+}
+
 template <int KJ>
 JSS_DEV void env_store(const JssParams &p, int env, int lane, const EnvRegs<KJ> &s) {
     int32_t *blk = p.state + (size_t)env * p.block_words;
@@ -689,11 +719,13 @@ JSS_DEV void jss_stage_instance(const JssParams &p, const JssInstDesc &d, uint16
     }
 }
 
-template <int KJ>
+template <int KJ, int MODE>
 JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstView &iv, int env, int lane,
                              float *scratch) {
     EnvRegs<KJ> s;
-    const int mode = a.mode;
+    // MODE is a compile-time kernel variant (the hot step kernel carries no policy /
+    // rollout / export code); JSS_MODE_RESET instantiates the rarely used rest
+    const int mode = (MODE == JSS_MODE_RESET) ? a.mode : MODE;
     if (mode == JSS_MODE_RESET) {
         if (a.env_mask && a.env_mask[env] == 0) return;
         env_reset_regs<KJ>(iv, s, lane);
@@ -717,9 +749,10 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
         if (lane == 0) p.done[env] = (s.flags & JSS_FLAG_DONE) ? 1 : 0;
         return;
     }
-    env_load<KJ>(p, iv, env, lane, s);
-    if (mode == JSS_MODE_EXPORT) { env_export<KJ>(p, iv, s, env, lane); return; }
     const uint64_t genv = p.env_id_base + (uint64_t)env;
+    if (mode == JSS_MODE_POLICY) env_load_for_policy<KJ>(p, iv, env, lane, s, a.rule);
+    else env_load<KJ>(p, iv, env, lane, s);
+    if (mode == JSS_MODE_EXPORT) { env_export<KJ>(p, iv, s, env, lane); return; }
     if (mode == JSS_MODE_POLICY) {
         const uint32_t h = jss_hash3(a.seed, genv, a.step_index);
         const int act = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h);
@@ -771,7 +804,7 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
     }
 }
 
-template <int KJ>
+template <int KJ, int MODE>
 __global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32)
 jss_env_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JSS_SMEM_DECL(jss_smem);
@@ -780,7 +813,7 @@ jss_env_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     uint16_t *sm_rem = reinterpret_cast<uint16_t *>(sm_len + sl.len_elems);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *scratch = reinterpret_cast<float *>(sm_rem + sl.rem_elems) + (size_t)warp * sl.scratch_words;
-    const bool want_rem = (a.mode == JSS_MODE_POLICY || a.mode == JSS_MODE_ROLLOUT) &&
+    const bool want_rem = (MODE == JSS_MODE_POLICY || MODE == JSS_MODE_ROLLOUT) &&
                           (a.rule == JSS_RULE_MWR || a.rule == JSS_RULE_LWR || a.rule == JSS_RULE_CR);
     int staged = -1;
     InstView iv;
@@ -798,7 +831,7 @@ jss_env_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
             staged = inst;
             __syncthreads();
         }
-        if (warp < count) jss_process_env<KJ>(p, a, iv, p.order[td.first + warp], lane, scratch);
+        if (warp < count) jss_process_env<KJ, MODE>(p, a, iv, p.order[td.first + warp], lane, scratch);
     }
 }
 
