@@ -254,6 +254,10 @@ int jss_load_instances(jss_t *h, int n_inst, const int32_t *jobs, const int32_t 
         d.max_time_op = (int32_t)hi.max_time_op;
         d.max_time_jobs = (int32_t)hi.max_time_jobs;
         d.sum_op = (int32_t)hi.sum_op;
+        d.r_mto = 1.0f / (float)d.max_time_op;
+        d.r_mtj = 1.0f / (float)d.max_time_jobs;
+        d.r_sop = 1.0f / (float)d.sum_op;
+        d.r_M = 1.0f / (float)d.M;
         h->insts[k] = hi;
         h->descs[k] = d;
     }

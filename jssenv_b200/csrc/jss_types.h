@@ -16,6 +16,8 @@ struct JssInstDesc {
     int32_t ops_off;                              // offsets into the pools, in elements
     int32_t len_off;
     int32_t rem_off;
+    // correctly rounded fp32 reciprocals of the four observation divisors (jss_div)
+    float r_mto, r_mtj, r_sop, r_M;
 };
 
 // ---- per-env state block in HBM (int32 words; every sub-array 16-byte aligned) ---
@@ -25,8 +27,8 @@ struct JssInstDesc {
 //   [3Jcap  , 4Jcap)   total_idle_time_jobs
 //   [4Jcap  , 5Jcap)   numerator of real_obs[:,4] (stale by design, jss_env.py:569-586)
 //   [5Jcap  , +Mcap)   time_until_available_machine
-//   then 4 words  legal ballots    L[i], bit l  <-> job KJ*l + i
-//        4 words  blocked ballots  B[i]  (action_illegal_no_op)
+//   then 8 words  = 32 bytes, byte l = lane l's job bits: bit i legal(job KJ*l+i),
+//                   bit 4+i blocked by a no-op (action_illegal_no_op)
 //        4 words  header: current_time_step, flags, episode_steps, episode_return_raw
 // Not stored because derivable: event queue, illegal_actions
 // [M][J], machine_legal, both counters, needed_machine_jobs, total_perform_op_time_jobs.

@@ -43,7 +43,7 @@ static inline float4 make_float4(float a, float b, float c, float d) { return fl
 namespace emu {
 extern thread_local dim3 threadIdx_, blockIdx_, blockDim_, gridDim_;
 extern void *smem_ptr;
-enum Op { OP_SHFL = 1, OP_SHFL_XOR, OP_BALLOT, OP_RED_MIN, OP_RED_MAX, OP_RED_ADD, OP_RED_OR, OP_SYNCWARP, OP_SYNCTHREADS };
+enum Op { OP_SHFL = 1, OP_SHFL_XOR, OP_SHFL_UP, OP_BALLOT, OP_RED_MIN, OP_RED_MAX, OP_RED_ADD, OP_RED_OR, OP_SYNCWARP, OP_SYNCTHREADS };
 uint64_t collective(int op, unsigned mask, uint64_t value, int arg);
 void launch_impl(void (*entry)(void *), void *args, dim3 grid, dim3 block, size_t smem);
 }  // namespace emu
@@ -62,6 +62,9 @@ template <typename T>
 static inline T __shfl_sync(unsigned mask, T v, int src) { return emu_unpack<T>(emu::collective(emu::OP_SHFL, mask, emu_pack(v), src & 31)); }
 template <typename T>
 static inline T __shfl_xor_sync(unsigned mask, T v, int x) { return emu_unpack<T>(emu::collective(emu::OP_SHFL_XOR, mask, emu_pack(v), x)); }
+template <typename T>
+static inline T __shfl_up_sync(unsigned mask, T v, unsigned d) { return emu_unpack<T>(emu::collective(emu::OP_SHFL_UP, mask, emu_pack(v), (int)d)); }
+static inline bool __any_sync(unsigned mask, bool pred) { return emu::collective(emu::OP_BALLOT, mask, pred ? 1 : 0, 0) != 0; }
 static inline unsigned __ballot_sync(unsigned mask, bool pred) { return (unsigned)emu::collective(emu::OP_BALLOT, mask, pred ? 1 : 0, 0); }
 static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) { return (unsigned)emu::collective(emu::OP_RED_MIN, mask, v, 0); }
 static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) { return (unsigned)emu::collective(emu::OP_RED_MAX, mask, v, 0); }
@@ -73,6 +76,8 @@ static inline void __syncthreads() { emu::collective(emu::OP_SYNCTHREADS, 0xffff
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline float __fdiv_rn(float a, float b) { return a / b; }  // IEEE fp32 divide, round-to-nearest
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }   // never contracted
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }       // single rounding
 template <typename T>
 static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <typename T>

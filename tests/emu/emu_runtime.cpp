@@ -67,7 +67,12 @@ void resolve_warp(int w) {
     Fiber *l = &fibers[(size_t)w * 32];
     const int op = l[0].op;
     for (int i = 0; i < 32; i++) {
-        if (l[i].op != op) die("lanes of one warp wait at different collectives (divergent collective)", w);
+        if (l[i].op != op) {
+            fprintf(stderr, "[jss emu] ops per lane:");
+            for (int k = 0; k < 32; k++) fprintf(stderr, " %d", l[k].op);
+            fprintf(stderr, "\n");
+            die("lanes of one warp wait at different collectives (divergent collective)", w);
+        }
         if (l[i].mask != 0xffffffffu) die("collective without a full mask", w);
     }
     uint64_t agg = 0;
@@ -83,6 +88,7 @@ void resolve_warp(int w) {
         switch (op) {
         case OP_SHFL: l[i].result = l[l[i].arg & 31].value; break;
         case OP_SHFL_XOR: l[i].result = l[(i ^ l[i].arg) & 31].value; break;
+        case OP_SHFL_UP: l[i].result = (i >= l[i].arg) ? l[i - l[i].arg].value : l[i].value; break;
         case OP_SYNCWARP: l[i].result = 0; break;
         default: l[i].result = agg; break;
         }
@@ -93,6 +99,8 @@ void resolve_warp(int w) {
 
 uint64_t collective(int op, unsigned mask, uint64_t value, int arg) {
     Fiber &f = fibers[cur];
+    static const bool trace = getenv("JSS_EMU_TRACE") != nullptr;
+    if (trace && (cur == 32 || cur == 33)) fprintf(stderr, "T%d op%d v=%llu a=%d\n", cur, op, (unsigned long long)value, arg);
     f.op = op; f.mask = mask; f.value = value; f.arg = arg; f.state = WAITING;
     if (_setjmp(f.jb) == 0) _longjmp(sched_jb, 1);
     return f.result;
