@@ -67,7 +67,7 @@ extern "C" {
 #define JSS_CREATE_AUTO_RESET 1u      /* step() on a done env resets it */
 #define JSS_CREATE_RECORD_SOLUTION 2u /* keep solution[N][Jmax][Mmax] start times (jss_env.py:163,454) */
 
-/* per-env flag bits in jss_buffers.flags */
+/* per-env flag bits (jss_buffers.flags_done >> 8) */
 #define JSS_FLAG_DONE 1u        /* _is_done() (jss_env.py:639-653) */
 #define JSS_FLAG_ERROR 2u       /* sticky until reset */
 #define JSS_FLAG_NOOP_LEGAL 4u  /* legal_actions[J] */
@@ -99,11 +99,14 @@ typedef struct jss_buffers {
     int32_t mask_stride;    /* bytes per action_mask row (>= J+1, multiple of 4) */
     uint8_t *action_mask;   /* [N][mask_stride]; bytes 0..J_i = legal_actions of env i (jss_env.py:133) */
     float *real_obs;        /* [N][J][7] fp32 (jss_env.py:102-111, 132)            */
+    int32_t scalar_stride;  /* bytes between consecutive envs in the five per-env scalar arrays below
+                               (they are fields of one 16-byte record per env, written with one store) */
+    int32_t reserved_;
     float *reward;          /* [N] scaled reward (jss_env.py:483-493)              */
     int32_t *reward_raw;    /* [N] reward before scaling; -hole for ACTION_ADVANCE */
-    uint8_t *done;          /* [N]                                                 */
+    uint8_t *done;          /* [N] 0/1 (low byte of flags_done)                    */
     int32_t *time;          /* [N] current_time_step (makespan once done)          */
-    uint32_t *flags;        /* [N] JSS_FLAG_*                                      */
+    uint32_t *flags_done;   /* [N] (JSS_FLAG_* << 8) | done                        */
     int32_t *solution;      /* [N][J][M] or NULL (JSS_CREATE_RECORD_SOLUTION)      */
     /* per-env episode statistics, updated when an episode ends */
     int32_t *episode_count;     /* [N] finished episodes               */

@@ -33,8 +33,9 @@ EXPORTED_SYMBOLS = (
 class JssBuffers(ctypes.Structure):
     _fields_ = [
         ("n_envs", c_int32), ("jobs_max", c_int32), ("machines_max", c_int32), ("mask_stride", c_int32),
-        ("action_mask", c_void_p), ("real_obs", c_void_p), ("reward", c_void_p), ("reward_raw", c_void_p),
-        ("done", c_void_p), ("time", c_void_p), ("flags", c_void_p), ("solution", c_void_p),
+        ("action_mask", c_void_p), ("real_obs", c_void_p), ("scalar_stride", c_int32), ("reserved_", c_int32),
+        ("reward", c_void_p), ("reward_raw", c_void_p),
+        ("done", c_void_p), ("time", c_void_p), ("flags_done", c_void_p), ("solution", c_void_p),
         ("episode_count", c_void_p), ("last_makespan", c_void_p), ("last_return", c_void_p),
         ("x_todo", c_void_p), ("x_tufco", c_void_p), ("x_idle_last", c_void_p), ("x_total_idle", c_void_p),
         ("x_col4", c_void_p), ("x_tuam", c_void_p), ("x_legal", c_void_p), ("x_blocked", c_void_p),

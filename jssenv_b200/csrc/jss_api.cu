@@ -55,6 +55,7 @@ struct jss_handle {
     JssParams p{};
     JssSmemLayout sl_norem{}, sl_rem{};
     int class_tile_begin[3] = {0, 0, 0}, class_tile_end[3] = {0, 0, 0};  // KJ = 1, 2, 4
+    int step_grid[3] = {0, 0, 0};
     std::vector<int32_t> env_inst;
 
     // pinned staging for jss_step_host
@@ -98,8 +99,34 @@ inline int kj_of(int J) { return J <= 32 ? 1 : (J <= 64 ? 2 : 4); }
 inline int class_of(int kj) { return kj == 1 ? 0 : (kj == 2 ? 1 : 2); }
 
 size_t smem_bytes(const JssSmemLayout &sl) {
-    return (size_t)sl.ops_elems * 2 + (size_t)sl.len_elems * 4 + (size_t)sl.rem_elems * 2 +
+    return sizeof(SmInst) + (size_t)sl.ops_elems * 2 + (size_t)sl.len_elems * 4 + (size_t)sl.rem_elems * 2 +
            (size_t)JSS_WARPS_PER_CTA * sl.scratch_words * 4;
+}
+size_t smem_bytes_step(const JssSmemLayout &sl) {
+    return sizeof(SmInst) + (size_t)sl.ops_elems * 2 + (size_t)sl.len_elems * 4 +
+           (size_t)JSS_WARPS_PER_CTA * (4 + sl.statein_words + sl.scratch_words) * 4;
+}
+
+template <int KJ>
+int launch_step(jss_t *h, const JssLaunch &a, cudaStream_t st) {
+    const int n_tiles = a.tile_end - a.tile_begin;
+    JssSmemLayout sl = h->sl_norem;
+    sl.statein_words = h->p.block_words;
+    const size_t smem = smem_bytes_step(sl);
+    auto kern = jss_step_kernel<KJ>;
+    int &grid = h->step_grid[KJ == 1 ? 0 : (KJ == 2 ? 1 : 2)];
+    if (grid == 0) {                                     // once per handle: opt-in smem + occupancy
+        if (smem > 48 * 1024)
+            JSS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        JSS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, JSS_WARPS_PER_CTA * 32, smem));
+        if (per_sm < 1) return fail(h, JSS_ERR_CUDA, "step kernel does not fit on an SM (smem %zu B)", smem);
+        grid = h->sm_count * per_sm;
+    }
+    JSS_LAUNCH(kern, std::min(n_tiles, grid), JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl);
+    JSS_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    return JSS_OK;
 }
 
 template <int KJ, int MODE>
@@ -121,7 +148,7 @@ template <int KJ>
 int launch_class(jss_t *h, const JssLaunch &a, const JssSmemLayout &sl, cudaStream_t st) {
     if (a.tile_end - a.tile_begin <= 0) return JSS_OK;
     switch (a.mode) {
-    case JSS_MODE_STEP: return launch_variant<KJ, JSS_MODE_STEP>(h, a, sl, st);
+    case JSS_MODE_STEP: return launch_step<KJ>(h, a, st);
     case JSS_MODE_POLICY: return launch_variant<KJ, JSS_MODE_POLICY>(h, a, sl, st);
     case JSS_MODE_ROLLOUT: return launch_variant<KJ, JSS_MODE_ROLLOUT>(h, a, sl, st);
     default: return launch_variant<KJ, JSS_MODE_RESET>(h, a, sl, st);   // reset / export / import
@@ -347,6 +374,11 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
     p.mask_stride = round_up(jmax + 1, 4);
     p.create_flags = (int32_t)h->create_flags;
     p.env_id_base = h->env_id_base;
+    {
+        bool uniform = true;
+        for (int e = 0; e < N; e++) uniform = uniform && env_to_inst[e] == env_to_inst[0];
+        p.uniform_inst = uniform ? env_to_inst[0] : -1;   // then `order` is the identity (stable sort)
+    }
     p.inst = h->d_inst; p.ops_pool = h->d_ops; p.len_pool = h->d_len; p.rem_pool = h->d_rem;
 
     h->sl_norem.ops_elems = round_up(ops_max, 8);
@@ -369,11 +401,7 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
     if ((rc = dev_alloc(h, &p.state, (size_t)N * p.block_words))) return rc;
     if ((rc = dev_alloc(h, &p.mask, (size_t)N * p.mask_stride))) return rc;
     if ((rc = dev_alloc(h, &p.obs, NJ * 7))) return rc;
-    if ((rc = dev_alloc(h, &p.reward, (size_t)N))) return rc;
-    if ((rc = dev_alloc(h, &p.reward_raw, (size_t)N))) return rc;
-    if ((rc = dev_alloc(h, &p.done, (size_t)N))) return rc;
-    if ((rc = dev_alloc(h, &p.time, (size_t)N))) return rc;
-    if ((rc = dev_alloc(h, &p.flags, (size_t)N))) return rc;
+    if ((rc = dev_alloc(h, &p.scalars, (size_t)N * 4))) return rc;
     if (h->create_flags & JSS_CREATE_RECORD_SOLUTION) {
         if ((rc = dev_alloc(h, &p.solution, NJ * mmax, false))) return rc;
         JSS_CUDA(h, cudaMemset(p.solution, 0xff, NJ * mmax * 4));  // -1
@@ -406,8 +434,11 @@ int jss_get_buffers(jss_t *h, jss_buffers *out) {
     memset(out, 0, sizeof *out);
     out->n_envs = p.n_envs; out->jobs_max = p.jobs_max; out->machines_max = p.machines_max;
     out->mask_stride = p.mask_stride;
-    out->action_mask = p.mask; out->real_obs = p.obs; out->reward = p.reward; out->reward_raw = p.reward_raw;
-    out->done = p.done; out->time = p.time; out->flags = p.flags; out->solution = p.solution;
+    out->action_mask = p.mask; out->real_obs = p.obs; out->solution = p.solution;
+    out->scalar_stride = 16;   // reward / reward_raw / time / flags_done are fields of one 16-byte record per env
+    out->reward = reinterpret_cast<float *>(p.scalars); out->reward_raw = p.scalars + 1;
+    out->time = p.scalars + 2; out->flags_done = reinterpret_cast<uint32_t *>(p.scalars + 3);
+    out->done = reinterpret_cast<uint8_t *>(p.scalars + 3);
     out->episode_count = p.episode_count; out->last_makespan = p.last_makespan; out->last_return = p.last_return;
     out->x_todo = p.x_todo; out->x_tufco = p.x_tufco; out->x_idle_last = p.x_idle_last;
     out->x_total_idle = p.x_total_idle; out->x_col4 = p.x_col4; out->x_tuam = p.x_tuam;
@@ -475,8 +506,10 @@ int jss_step_host(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, flo
                                       (size_t)p.jobs_max + 1, N, cudaMemcpyDeviceToHost, st));
     if (obs_host)
         JSS_CUDA(h, cudaMemcpyAsync(obs_host, p.obs, N * p.jobs_max * 7 * 4, cudaMemcpyDeviceToHost, st));
-    if (reward_host) JSS_CUDA(h, cudaMemcpyAsync(reward_host, p.reward, N * 4, cudaMemcpyDeviceToHost, st));
-    if (done_host) JSS_CUDA(h, cudaMemcpyAsync(done_host, p.done, N, cudaMemcpyDeviceToHost, st));
+    if (reward_host)
+        JSS_CUDA(h, cudaMemcpy2DAsync(reward_host, 4, p.scalars, 16, 4, N, cudaMemcpyDeviceToHost, st));
+    if (done_host)
+        JSS_CUDA(h, cudaMemcpy2DAsync(done_host, 1, p.scalars + 3, 16, 1, N, cudaMemcpyDeviceToHost, st));
     JSS_CUDA(h, cudaStreamSynchronize(st));
     return JSS_OK;
 }

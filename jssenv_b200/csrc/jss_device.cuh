@@ -24,6 +24,7 @@
 // product library.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/jss_b200.h"
 #include "jss_rng.h"
@@ -36,13 +37,19 @@
 #define JSS_DEV __device__ __forceinline__
 #endif
 
-struct InstView {  // instance tables staged in shared memory + per-instance scalars
-    const uint16_t *ops;
-    const int32_t *len;
-    const uint16_t *rem;
+// Per-instance scalars live in shared memory next to the staged tables (CTA-uniform, re-read
+// with cheap broadcast LDS instead of pinning ~14 registers per thread).
+struct SmInst {
     int J, M, max_time_op, max_time_jobs, sum_op;
     float f_mto, f_mtj, f_sop, f_M;       // the divisors as floats ...
     float r_mto, r_mtj, r_sop, r_M;       // ... and their correctly rounded reciprocals
+    int pad_[3];
+};
+struct InstView {  // instance tables staged in shared memory
+    const uint16_t *ops;
+    const int32_t *len;
+    const uint16_t *rem;
+    const SmInst *si;
 };
 
 template <int KJ>
@@ -75,7 +82,7 @@ JSS_DEV uint32_t jss_bit(uint32_t mask, uint32_t pos) {
 }
 JSS_DEV uint32_t jss_op_m(uint32_t op) { return op >> JSS_OP_SHIFT; }
 JSS_DEV int jss_op_d(uint32_t op) { return (int)(op & JSS_OP_DMASK); }
-JSS_DEV uint32_t jss_op_at(const InstView &iv, int j, int ts) { return iv.ops[j * iv.M + ts]; }
+JSS_DEV uint32_t jss_op_at(const InstView &iv, int j, int ts) { return iv.ops[j * iv.si->M + ts]; }
 template <int KJ>
 JSS_DEV constexpr uint32_t jss_legal_mask() { return (1u << KJ) - 1u; }
 
@@ -88,6 +95,49 @@ JSS_DEV float jss_div(float x, float y, float ry) {
     const float r = __fmaf_rn(-q, y, x);
     return __fmaf_rn(r, ry, q);
 }
+
+// ---- TMA (cp.async.bulk) + mbarrier helpers -----------------------------------------------
+// The state block of the NEXT env of a warp is prefetched into the warp's shared-memory
+// buffer by one bulk copy (global -> shared, completion on an mbarrier) while the current env
+// is simulated; an env's observation rows leave shared memory with one bulk copy
+// (shared -> global).  Sizes/addresses are multiples of 16 bytes by construction.
+#ifndef JSS_EMU
+JSS_DEV uint32_t jss_smem_addr(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+JSS_DEV void jss_mbar_init(uint64_t *mbar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(jss_smem_addr(mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+JSS_DEV void jss_bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *mbar) {
+    const uint32_t mb = jss_smem_addr(mbar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(jss_smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(mb) : "memory");
+}
+JSS_DEV void jss_mbar_wait(uint64_t *mbar, uint32_t phase) {
+    const uint32_t mb = jss_smem_addr(mbar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(mb), "r"(phase) : "memory");
+    } while (!ok);
+}
+JSS_DEV void jss_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+JSS_DEV void jss_bulk_store(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gmem_dst), "r"(jss_smem_addr(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+JSS_DEV void jss_bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+JSS_DEV void jss_bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+#else   // host emulation (tests/emu): synchronous copies; the waits are warp rendezvous points
+JSS_DEV void jss_mbar_init(uint64_t *mbar) { *mbar = 0; }
+JSS_DEV void jss_bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *) { memcpy(smem_dst, gmem_src, bytes); }
+JSS_DEV void jss_mbar_wait(uint64_t *, uint32_t) { __syncwarp(); }
+JSS_DEV void jss_fence_async_smem() {}
+JSS_DEV void jss_bulk_store(void *gmem_dst, const void *smem_src, uint32_t bytes) { memcpy(gmem_dst, smem_src, bytes); }
+JSS_DEV void jss_bulk_store_wait_read() {}
+JSS_DEV void jss_bulk_store_wait_all() {}
+#endif
 
 // vector access to a lane's KJ-word slice
 template <int KJ>
@@ -120,23 +170,22 @@ JSS_DEV void jss_st<4>(int32_t *p, const int (&o)[4]) {
 // last job) hold todo == M, i.e. they behave like finished jobs everywhere.
 template <int KJ>
 JSS_DEV void env_derive_ops(const InstView &iv, EnvRegs<KJ> &s, int lane) {
-    const int row = KJ * lane * iv.M;
+    const int row = KJ * lane * iv.si->M;
 #pragma unroll
     for (int i = 0; i < KJ; i++)
-        s.op[i] = (s.todo[i] < iv.M) ? (uint32_t)iv.ops[row + i * iv.M + s.todo[i]] : JSS_OP_NONE;
+        s.op[i] = (s.todo[i] < iv.si->M) ? (uint32_t)iv.ops[row + i * iv.si->M + s.todo[i]] : JSS_OP_NONE;
 }
 
 template <int KJ>
 JSS_DEV void env_clear_jobs(const InstView &iv, EnvRegs<KJ> &s) {
 #pragma unroll
-    for (int i = 0; i < KJ; i++) { s.todo[i] = iv.M; s.tufco[i] = 0; s.idle_last[i] = 0; s.total_idle[i] = 0; s.col4[i] = 0; }
+    for (int i = 0; i < KJ; i++) { s.todo[i] = iv.si->M; s.tufco[i] = 0; s.idle_last[i] = 0; s.total_idle[i] = 0; s.col4[i] = 0; }
 }
 
 template <int KJ>
-JSS_DEV void env_load(const JssParams &p, const InstView &iv, int env, int lane, EnvRegs<KJ> &s) {
-    const int32_t *blk = p.state + (size_t)env * p.block_words;
+JSS_DEV void env_load_from(const JssParams &p, const InstView &iv, const int32_t *blk, int lane, EnvRegs<KJ> &s) {
     const int Jc = p.Jcap;
-    if (KJ * lane < iv.J) {
+    if (KJ * lane < iv.si->J) {
         const int32_t *q = blk + KJ * lane;
         jss_ld<KJ>(q, s.todo);
         jss_ld<KJ>(q + Jc, s.tufco);
@@ -147,11 +196,15 @@ JSS_DEV void env_load(const JssParams &p, const InstView &iv, int env, int lane,
         env_clear_jobs<KJ>(iv, s);
     }
     const int32_t *tail = blk + 5 * Jc;
-    s.tuam = (lane < iv.M) ? tail[lane] : 0;
+    s.tuam = (lane < iv.si->M) ? tail[lane] : 0;
     s.lb = reinterpret_cast<const uint8_t *>(tail + p.Mcap)[lane];
     const int4 h4 = *reinterpret_cast<const int4 *>(tail + p.Mcap + 8);
     s.t = h4.x; s.flags = (uint32_t)h4.y; s.ep_steps = h4.z; s.ep_return = h4.w;
     env_derive_ops<KJ>(iv, s, lane);
+}
+template <int KJ>
+JSS_DEV void env_load(const JssParams &p, const InstView &iv, int env, int lane, EnvRegs<KJ> &s) {
+    env_load_from<KJ>(p, iv, p.state + (size_t)env * p.block_words, lane, s);
 }
 
 // policy kernels read only what the rule looks at: bits + header always, todo for every
@@ -162,7 +215,7 @@ JSS_DEV void env_load_for_policy(const JssParams &p, const InstView &iv, int env
     const int32_t *blk = p.state + (size_t)env * p.block_words;
     const int Jc = p.Jcap;
     env_clear_jobs<KJ>(iv, s);
-    if (rule != JSS_RULE_RANDOM && KJ * lane < iv.J) {
+    if (rule != JSS_RULE_RANDOM && KJ * lane < iv.si->J) {
         jss_ld<KJ>(blk + KJ * lane, s.todo);
         if (rule == JSS_RULE_FIFO) jss_ld<KJ>(blk + 2 * Jc + KJ * lane, s.idle_last);
     }
@@ -186,7 +239,7 @@ JSS_DEV void env_store(const JssParams &p, const InstView &iv, int env, int lane
     // before any lane overwrites the block: paths such as the auto-reset have no
     // collective between load and store
     __syncwarp();
-    if (KJ * lane < iv.J) {
+    if (KJ * lane < iv.si->J) {
         int32_t *q = blk + KJ * lane;
         jss_st<KJ>(q, s.todo);
         jss_st<KJ>(q + Jc, s.tufco);
@@ -195,7 +248,7 @@ JSS_DEV void env_store(const JssParams &p, const InstView &iv, int env, int lane
         jss_st<KJ>(q + 4 * Jc, s.col4);
     }
     int32_t *tail = blk + 5 * Jc;
-    if (lane < iv.M) tail[lane] = s.tuam;
+    if (lane < iv.si->M) tail[lane] = s.tuam;
     reinterpret_cast<uint8_t *>(tail + p.Mcap)[lane] = (uint8_t)s.lb;
     if (lane == 0)
         *reinterpret_cast<int4 *>(tail + p.Mcap + 8) = make_int4(s.t, (int)s.flags, s.ep_steps, s.ep_return);
@@ -207,8 +260,8 @@ JSS_DEV void env_reset_regs(const InstView &iv, EnvRegs<KJ> &s, int lane) {
     s.lb = 0u;
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
-        const bool valid = KJ * lane + i < iv.J;
-        s.todo[i] = valid ? 0 : iv.M;
+        const bool valid = KJ * lane + i < iv.si->J;
+        s.todo[i] = valid ? 0 : iv.si->M;
         s.tufco[i] = 0; s.idle_last[i] = 0; s.total_idle[i] = 0; s.col4[i] = 0;
         if (valid) s.lb |= 1u << i;               // every job legal, no-op illegal (:160-161)
     }
@@ -224,9 +277,9 @@ JSS_DEV int env_advance(const InstView &iv, EnvRegs<KJ> &s, int lane) {
     const int tuam_old = s.tuam;
     const int diff = (int)__reduce_min_sync(JSS_FULL, (unsigned)(tuam_old > 0 ? tuam_old : JSS_INF));
     const int gap = diff - tuam_old;                      // > 0 only for machines idle before the event
-    const int hole = (int)__reduce_add_sync(JSS_FULL, (unsigned)((lane < iv.M && gap > 0) ? gap : 0));
+    const int hole = (int)__reduce_add_sync(JSS_FULL, (unsigned)((lane < iv.si->M && gap > 0) ? gap : 0));
     s.t += diff;
-    const int row = KJ * lane * iv.M;
+    const int row = KJ * lane * iv.si->M;
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
         const int was = s.tufco[i];
@@ -239,9 +292,9 @@ JSS_DEV int env_advance(const InstView &iv, EnvRegs<KJ> &s, int lane) {
                 s.idle_last[i] = diff - was;
                 s.todo[i] += 1;
                 finished = true;
-                s.op[i] = (s.todo[i] < iv.M) ? (uint32_t)iv.ops[row + i * iv.M + s.todo[i]] : JSS_OP_NONE;
+                s.op[i] = (s.todo[i] < iv.si->M) ? (uint32_t)iv.ops[row + i * iv.si->M + s.todo[i]] : JSS_OP_NONE;
             }
-        } else if (s.todo[i] < iv.M) {                    // waiting (:594)
+        } else if (s.todo[i] < iv.si->M) {                    // waiting (:594)
             s.total_idle[i] += diff;
             s.idle_last[i] += diff;
         }
@@ -249,11 +302,11 @@ JSS_DEV int env_advance(const InstView &iv, EnvRegs<KJ> &s, int lane) {
         const int tq = __shfl_sync(JSS_FULL, tuam_old, (int)(jss_op_m(s.op[i]) & 31u));
         if (finished) {
             const int w = tq - diff;
-            s.col4[i] = (s.op[i] != JSS_OP_NONE) ? (w > 0 ? w : 0) : iv.max_time_op;   // max_time_op encodes 1.0 (:586)
+            s.col4[i] = (s.op[i] != JSS_OP_NONE) ? (w > 0 ? w : 0) : iv.si->max_time_op;   // max_time_op encodes 1.0 (:586)
         }
     }
     s.tuam = gap < 0 ? -gap : 0;
-    const uint32_t free_m = __ballot_sync(JSS_FULL, lane < iv.M && s.tuam == 0);
+    const uint32_t free_m = __ballot_sync(JSS_FULL, lane < iv.si->M && s.tuam == 0);
 #pragma unroll
     for (int i = 0; i < KJ; i++)                          // legalisation (:616-634)
         if (jss_bit(free_m, jss_op_m(s.op[i])) && !(s.lb & (16u << i))) s.lb |= 1u << i;
@@ -276,17 +329,17 @@ JSS_DEV void env_prioritize(const InstView &iv, EnvRegs<KJ> &s, int lane) {
     uint32_t fin = 0u, fin_m = 0u;                        // my legal FINAL ops / their machines
 #pragma unroll
     for (int i = 0; i < KJ; i++)
-        if ((s.lb & (1u << i)) && s.todo[i] == iv.M - 1) { fin |= 1u << i; fin_m |= 1u << (jss_op_m(s.op[i]) & 31u); }
+        if ((s.lb & (1u << i)) && s.todo[i] == iv.si->M - 1) { fin |= 1u << i; fin_m |= 1u << (jss_op_m(s.op[i]) & 31u); }
     fin_m = __reduce_or_sync(JSS_FULL, fin_m);
     if (fin_m == 0u) return;                              // nothing can be de-legalised
-    const uint32_t free_m = __ballot_sync(JSS_FULL, lane < iv.M && s.tuam == 0);
+    const uint32_t free_m = __ballot_sync(JSS_FULL, lane < iv.si->M && s.tuam == 0);
     int cand_d[KJ];                                       // duration if legal non-final op whose NEXT machine is free
-    const int row = KJ * lane * iv.M;
+    const int row = KJ * lane * iv.si->M;
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
         cand_d[i] = JSS_INF;
         if ((s.lb & (1u << i)) && !(fin & (1u << i))) {
-            const uint32_t nxt = iv.ops[row + i * iv.M + s.todo[i] + 1];
+            const uint32_t nxt = iv.ops[row + i * iv.si->M + s.todo[i] + 1];
             if (jss_bit(free_m, jss_op_m(nxt))) cand_d[i] = jss_op_d(s.op[i]);   // :234-239
         }
     }
@@ -318,7 +371,7 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
     const int next_event = s.t + (int)mn;                                        // :293
     int maxh = s.t;                                                              // :296
     int lm0 = -1, lm1 = -1, lm2 = -1;                   // the <= 3 legal machines and their horizons
-    const int hinit = s.t + iv.max_time_op;             // :300-302
+    const int hinit = s.t + iv.si->max_time_op;             // :300-302
     int h0 = hinit, h1 = hinit, h2 = hinit;
     // pass 1 (:305-321): legal jobs in ascending job index = ascending lane, then slot
     uint32_t lanes = __ballot_sync(JSS_FULL, (s.lb & jss_legal_mask<KJ>()) != 0u);
@@ -347,18 +400,18 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
     __syncwarp();
     // pass 2 (:324-401): jobs that are not legal now but may need a legal machine soon
     uint32_t want = 0u;
-    const int row = KJ * lane * iv.M;
+    const int row = KJ * lane * iv.si->M;
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
         // countdown of the job's current machine (case 2, :374-377)
         const int tq = __shfl_sync(JSS_FULL, s.tuam, (int)(jss_op_m(s.op[i]) & 31u));
-        if (!(s.lb & (1u << i)) && s.todo[i] < iv.M) {
+        if (!(s.lb & (1u << i)) && s.todo[i] < iv.si->M) {
             int ts, tm;
             if (s.tufco[i] > 0) { ts = s.todo[i] + 1; tm = s.t + s.tufco[i]; }      // case 1 (:327-337); a running
             else if (!(s.lb & (16u << i))) { ts = s.todo[i]; tm = s.t + tq; }       // last op walks nothing either way
-            else { ts = iv.M; tm = 0; }                                             // case 2 (:366-377) / blocked
-            const uint16_t *o_ptr = iv.ops + row + i * iv.M;
-            while (ts < iv.M - 1 && maxh > tm) {                                    // :340-342 / :380-382
+            else { ts = iv.si->M; tm = 0; }                                             // case 2 (:366-377) / blocked
+            const uint16_t *o_ptr = iv.ops + row + i * iv.si->M;
+            while (ts < iv.si->M - 1 && maxh > tm) {                                    // :340-342 / :380-382
                 const uint32_t o = o_ptr[ts];
                 if (hz[jss_op_m(o)] > tm) want |= 1u << jss_op_m(o);                // machine_next.add (:351 / :391)
                 tm += jss_op_d(o);
@@ -372,24 +425,24 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
 }
 
 // ---- observation / mask / reward (jss_env.py:102-134, 483-493) ---------------------
-template <int KJ>
+template <int KJ, bool BULK = false>
 JSS_DEV void env_emit_obs(const JssParams &p, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane,
                           float *scratch) {
-    if (KJ * lane < iv.J) {
+    if (KJ * lane < iv.si->J) {
         float v[KJ * 7];
 #pragma unroll
         for (int i = 0; i < KJ; i++) {
             // total_perform_op_time_jobs == t - total_idle while the job is unfinished,
             // jobs_length[j] afterwards (every advance adds `difference` to exactly one of
             // the two counters until the job completes)
-            const int perf = (s.todo[i] < iv.M) ? s.t - s.total_idle[i] : iv.len[KJ * lane + i];
+            const int perf = (s.todo[i] < iv.si->M) ? s.t - s.total_idle[i] : iv.len[KJ * lane + i];
             v[7 * i + 0] = (s.lb & (1u << i)) ? 1.0f : 0.0f;
-            v[7 * i + 1] = jss_div((float)s.tufco[i], iv.f_mto, iv.r_mto);
-            v[7 * i + 2] = jss_div((float)s.todo[i], iv.f_M, iv.r_M);
-            v[7 * i + 3] = jss_div((float)perf, iv.f_mtj, iv.r_mtj);
-            v[7 * i + 4] = jss_div((float)s.col4[i], iv.f_mto, iv.r_mto);
-            v[7 * i + 5] = jss_div((float)s.idle_last[i], iv.f_sop, iv.r_sop);
-            v[7 * i + 6] = jss_div((float)s.total_idle[i], iv.f_sop, iv.r_sop);
+            v[7 * i + 1] = jss_div((float)s.tufco[i], iv.si->f_mto, iv.si->r_mto);
+            v[7 * i + 2] = jss_div((float)s.todo[i], iv.si->f_M, iv.si->r_M);
+            v[7 * i + 3] = jss_div((float)perf, iv.si->f_mtj, iv.si->r_mtj);
+            v[7 * i + 4] = jss_div((float)s.col4[i], iv.si->f_mto, iv.si->r_mto);
+            v[7 * i + 5] = jss_div((float)s.idle_last[i], iv.si->f_sop, iv.si->r_sop);
+            v[7 * i + 6] = jss_div((float)s.total_idle[i], iv.si->f_sop, iv.si->r_sop);
         }
         // stage the lane's 7*KJ floats (one contiguous, bank-conflict-free run per lane) ...
         float *mine = scratch + 7 * KJ * lane;
@@ -405,10 +458,17 @@ JSS_DEV void env_emit_obs(const JssParams &p, const InstView &iv, const EnvRegs<
             for (int q = 0; q < 7; q++) mine[q] = v[q];
         }
     }
+    float *dst = p.obs + (size_t)env * p.jobs_max * 7;
+    const int n = iv.si->J * 7;
+    if (BULK && (n & 3) == 0 && (p.jobs_max & 3) == 0) {
+        // ... and hand the env's J*7 floats to the TMA engine: one bulk copy shared -> global
+        jss_fence_async_smem();          // make the generic-proxy writes visible to the async proxy
+        __syncwarp();
+        if (lane == 0) jss_bulk_store(dst, scratch, (uint32_t)n * 4u);
+        return;                          // the caller waits (wait_group.read) before reusing `scratch`
+    }
     __syncwarp();
     // ... and stream the J*7 floats of the env out with fully coalesced stores
-    float *dst = p.obs + (size_t)env * p.jobs_max * 7;
-    const int n = iv.J * 7;
     int done_elems = 0;
     if ((p.jobs_max & 3) == 0) {
         const int n4 = n >> 2;
@@ -425,28 +485,28 @@ JSS_DEV void env_emit_mask(const JssParams &p, const InstView &iv, const EnvRegs
                            bool noop) {
     uint8_t *row = p.mask + (size_t)env * p.mask_stride;
     const int j0 = KJ * lane;
-    if (j0 <= iv.J) {
+    if (j0 <= iv.si->J) {
         // spread the legal bits to bytes: bit i -> byte i
         uint32_t w = 0u;
 #pragma unroll
         for (int i = 0; i < KJ; i++) w |= ((s.lb >> i) & 1u) << (8 * i);
-        if (iv.J - j0 < KJ) w |= (noop ? 1u : 0u) << (8 * (iv.J - j0));     // byte J is the no-op flag
+        if (iv.si->J - j0 < KJ) w |= (noop ? 1u : 0u) << (8 * (iv.si->J - j0));     // byte J is the no-op flag
         if (KJ == 4) *reinterpret_cast<uint32_t *>(row + j0) = w;
         else if (KJ == 2) *reinterpret_cast<uint16_t *>(row + j0) = (uint16_t)w;
         else row[j0] = (uint8_t)w;
     }
-    if (iv.J == 32 * KJ && lane == 0) row[iv.J] = noop ? 1 : 0;   // no lane owns byte J
+    if (iv.si->J == 32 * KJ && lane == 0) row[iv.si->J] = noop ? 1 : 0;   // no lane owns byte J
 }
 
+// reward / raw reward / time / (flags << 8 | done) of an env are ONE 16-byte record, so the
+// per-step scalar outputs cost a single store (the API exposes them as strided arrays)
 template <int KJ>
 JSS_DEV void env_emit_scalars(const JssParams &p, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane,
                               int raw_reward) {
     if (lane == 0) {
-        p.reward[env] = jss_div((float)raw_reward, iv.f_mto, iv.r_mto);   // :483-493
-        p.reward_raw[env] = raw_reward;
-        p.done[env] = (s.flags & JSS_FLAG_DONE) ? 1 : 0;
-        p.time[env] = s.t;
-        p.flags[env] = s.flags;
+        const float r = jss_div((float)raw_reward, iv.si->f_mto, iv.si->r_mto);   // :483-493
+        reinterpret_cast<int4 *>(p.scalars)[env] =
+            make_int4(__float_as_int(r), raw_reward, s.t, (int)((s.flags << 8) | (s.flags & JSS_FLAG_DONE)));
     }
 }
 
@@ -490,7 +550,7 @@ JSS_DEV bool env_step(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, in
     }
     constexpr uint32_t LM = jss_legal_mask<KJ>();
     int holes = 0;
-    if (action == JSS_ACTION_ADVANCE || action == iv.J) {
+    if (action == JSS_ACTION_ADVANCE || action == iv.si->J) {
         if (!__any_sync(JSS_FULL, s.tuam > 0)) { s.flags |= JSS_FLAG_ERROR; return false; }   // IndexError at :517
         if (action == JSS_ACTION_ADVANCE) {              // raw increase_time_step()
             raw_reward = -env_advance<KJ>(iv, s, lane);
@@ -505,7 +565,7 @@ JSS_DEV bool env_step(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, in
         if (none) s.flags |= JSS_FLAG_ERROR;             // the reference raises here (empty queue)
         raw_reward = -holes;
     } else {                                             // job allocation (:441-481)
-        if (action < 0 || action > iv.J) { s.flags |= JSS_FLAG_ERROR; return false; }
+        if (action < 0 || action > iv.si->J) { s.flags |= JSS_FLAG_ERROR; return false; }
         const int la = action / KJ, ia = action % KJ;
         const uint32_t opa = __shfl_sync(JSS_FULL, jss_sel<KJ>(s.op, ia), la);
         const uint32_t bits_a = __shfl_sync(JSS_FULL, s.lb, la);
@@ -559,11 +619,11 @@ JSS_DEV int env_select_action(const InstView &iv, const EnvRegs<KJ> &s, int lane
     const int njobs = (int)__shfl_sync(JSS_FULL, incl, 31);
     const bool noop = (s.flags & JSS_FLAG_NOOP_LEGAL) != 0u;
     if (s.flags & JSS_FLAG_DONE) return 0;               // ignored by step (auto-reset or frozen)
-    if (njobs == 0) return noop ? iv.J : JSS_ACTION_SKIP;   // "only the no-op is legal" (e.g. :96-97)
+    if (njobs == 0) return noop ? iv.si->J : JSS_ACTION_SKIP;   // "only the no-op is legal" (e.g. :96-97)
     if (rule == JSS_RULE_RANDOM) {
         // uniform over the set bits of action_mask, indexed in ascending action order
         const uint32_t r = jss_pick(h, (uint32_t)(njobs + (noop ? 1 : 0)));
-        if ((int)r == njobs) return iv.J;
+        if ((int)r == njobs) return iv.si->J;
         const uint32_t before = incl - mine;
         const bool own = r >= before && r < incl;
         int act = 0;
@@ -585,7 +645,7 @@ JSS_DEV int env_select_action(const InstView &iv, const EnvRegs<KJ> &s, int lane
             const int j = KJ * lane + i;
             if (s.lb & (1u << i)) {
                 const double due = (double)iv.len[j] * 1.5;                          // :357-360
-                const int remaining = iv.rem[j * (iv.M + 1) + s.todo[i]];            // :387-388
+                const int remaining = iv.rem[j * (iv.si->M + 1) + s.todo[i]];            // :387-388
                 const double ratio = remaining > 0 ? (due - (double)s.t) / (double)remaining : 1.0 / 0.0;
                 if (ratio < key) { key = ratio; kj = j; }                            // strict <, first index wins
             }
@@ -609,8 +669,8 @@ JSS_DEV int env_select_action(const InstView &iv, const EnvRegs<KJ> &s, int lane
                 if (rule == JSS_RULE_SPT) key = (uint32_t)jss_op_d(s.op[i]);                    // :105-108
                 else if (rule == JSS_RULE_FIFO) key = (uint32_t)s.idle_last[i];                 // :146-148
                 else if (rule == JSS_RULE_MWR || rule == JSS_RULE_LWR)
-                    key = iv.rem[j * (iv.M + 1) + s.todo[i]];                                   // :188-191 / :231-234
-                else key = (uint32_t)(iv.M - s.todo[i]);                                        // :273 / :314
+                    key = iv.rem[j * (iv.si->M + 1) + s.todo[i]];                                   // :188-191 / :231-234
+                else key = (uint32_t)(iv.si->M - s.todo[i]);                                        // :273 / :314
                 const uint32_t c = minimise ? ((key << 8) | (uint32_t)j) : ((key << 8) | (uint32_t)(255 - j));
                 comp = minimise ? min(comp, c) : max(comp, c);
             }
@@ -618,7 +678,7 @@ JSS_DEV int env_select_action(const InstView &iv, const EnvRegs<KJ> &s, int lane
         comp = minimise ? __reduce_min_sync(JSS_FULL, comp) : __reduce_max_sync(JSS_FULL, comp);
         best = minimise ? (int)(comp & 255u) : 255 - (int)(comp & 255u);
     }
-    if (noop && coin_mode == JSS_COIN_DEVICE && h < JSS_COIN_THRESHOLD) return iv.J;   // e.g. :113-114
+    if (noop && coin_mode == JSS_COIN_DEVICE && h < JSS_COIN_THRESHOLD) return iv.si->J;   // e.g. :113-114
     return best;
 }
 
@@ -629,7 +689,7 @@ JSS_DEV void env_export(const JssParams &p, const InstView &iv, const EnvRegs<KJ
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
         const int j = KJ * lane + i;
-        if (j < iv.J) {
+        if (j < iv.si->J) {
             p.x_todo[jb + j] = s.todo[i]; p.x_tufco[jb + j] = s.tufco[i];
             p.x_idle_last[jb + j] = s.idle_last[i]; p.x_total_idle[jb + j] = s.total_idle[i];
             p.x_col4[jb + j] = s.col4[i];
@@ -637,8 +697,11 @@ JSS_DEV void env_export(const JssParams &p, const InstView &iv, const EnvRegs<KJ
             p.x_blocked[jb + j] = (uint8_t)((s.lb >> (4 + i)) & 1u);
         }
     }
-    if (lane < iv.M) p.x_tuam[(size_t)env * p.machines_max + lane] = s.tuam;
-    if (lane == 0) { p.time[env] = s.t; p.flags[env] = s.flags; }
+    if (lane < iv.si->M) p.x_tuam[(size_t)env * p.machines_max + lane] = s.tuam;
+    if (lane == 0) {
+        p.scalars[4 * (size_t)env + 2] = s.t;
+        p.scalars[4 * (size_t)env + 3] = (int32_t)((s.flags << 8) | (s.flags & JSS_FLAG_DONE));
+    }
 }
 
 template <int KJ>
@@ -648,8 +711,8 @@ JSS_DEV void env_import(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, 
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
         const int j = KJ * lane + i;
-        const bool valid = j < iv.J;
-        s.todo[i] = valid ? p.x_todo[jb + j] : iv.M;
+        const bool valid = j < iv.si->J;
+        s.todo[i] = valid ? p.x_todo[jb + j] : iv.si->M;
         s.tufco[i] = valid ? p.x_tufco[jb + j] : 0;
         s.idle_last[i] = valid ? p.x_idle_last[jb + j] : 0;
         s.total_idle[i] = valid ? p.x_total_idle[jb + j] : 0;
@@ -657,20 +720,29 @@ JSS_DEV void env_import(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, 
         if (valid && p.x_legal[jb + j] != 0) s.lb |= 1u << i;
         if (valid && p.x_blocked[jb + j] != 0) s.lb |= 16u << i;
     }
-    s.tuam = lane < iv.M ? p.x_tuam[(size_t)env * p.machines_max + lane] : 0;
-    s.t = p.time[env];
-    s.flags = p.flags[env];
+    s.tuam = lane < iv.si->M ? p.x_tuam[(size_t)env * p.machines_max + lane] : 0;
+    s.t = p.scalars[4 * (size_t)env + 2];
+    s.flags = (uint32_t)p.scalars[4 * (size_t)env + 3] >> 8;
     env_derive_ops<KJ>(iv, s, lane);
 }
 
 // ---- CTA-level driver -----------------------------------------------------------------------
 struct JssSmemLayout {      // element counts; every region starts 16-byte aligned
     int32_t ops_elems, len_elems, rem_elems, scratch_words;
+    int32_t statein_words;  // step kernel only: per-warp state-block prefetch buffer
 };
 
-JSS_DEV void jss_stage_instance(const JssParams &p, const JssInstDesc &d, uint16_t *sm_ops, int32_t *sm_len,
-                                uint16_t *sm_rem, bool want_rem) {
+JSS_DEV void jss_stage_instance(const JssParams &p, const JssInstDesc &d, SmInst *si, uint16_t *sm_ops,
+                                int32_t *sm_len, uint16_t *sm_rem, bool want_rem, bool want_tables = true) {
     const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) {
+        si->J = d.J; si->M = d.M; si->max_time_op = d.max_time_op; si->max_time_jobs = d.max_time_jobs;
+        si->sum_op = d.sum_op;
+        si->f_mto = (float)d.max_time_op; si->f_mtj = (float)d.max_time_jobs; si->f_sop = (float)d.sum_op;
+        si->f_M = (float)d.M;
+        si->r_mto = d.r_mto; si->r_mtj = d.r_mtj; si->r_sop = d.r_sop; si->r_M = d.r_M;
+    }
+    if (!want_tables) return;
     {   // pools are padded so whole uint4 copies stay in-bounds
         const uint4 *src = reinterpret_cast<const uint4 *>(p.ops_pool + d.ops_off);
         uint4 *dst = reinterpret_cast<uint4 *>(sm_ops);
@@ -691,10 +763,10 @@ JSS_DEV void jss_stage_instance(const JssParams &p, const JssInstDesc &d, uint16
     }
 }
 
-template <int KJ>
+template <int KJ, bool BULK = false>
 JSS_DEV void env_emit_all(const JssParams &p, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane,
                           float *scratch, int raw) {
-    env_emit_obs<KJ>(p, iv, s, env, lane, scratch);
+    env_emit_obs<KJ, BULK>(p, iv, s, env, lane, scratch);
     env_emit_mask<KJ>(p, iv, s, env, lane, (s.flags & JSS_FLAG_NOOP_LEGAL) != 0u);
     env_emit_scalars<KJ>(p, iv, s, env, lane, raw);
 }
@@ -725,7 +797,7 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
         env_store<KJ>(p, iv, env, lane, s);
         env_emit_obs<KJ>(p, iv, s, env, lane, scratch);
         env_emit_mask<KJ>(p, iv, s, env, lane, (s.flags & JSS_FLAG_NOOP_LEGAL) != 0u);
-        if (lane == 0) p.done[env] = (s.flags & JSS_FLAG_DONE) ? 1 : 0;
+        if (lane == 0) p.scalars[4 * (size_t)env + 3] = (int32_t)((s.flags << 8) | (s.flags & JSS_FLAG_DONE));
         return;
     }
     const uint64_t genv = p.env_id_base + (uint64_t)env;
@@ -749,7 +821,8 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
         } else if (s.flags != flags_in) {                // only the sticky error bit changed
             if (lane == 0) {
                 p.state[(size_t)env * p.block_words + 5 * p.Jcap + p.Mcap + 8 + JSS_HDR_FLAGS] = (int32_t)s.flags;
-                p.flags[env] = s.flags; p.reward[env] = 0.0f; p.reward_raw[env] = 0;
+                reinterpret_cast<int4 *>(p.scalars)[env] =
+                    make_int4(0, 0, s.t, (int)((s.flags << 8) | (s.flags & JSS_FLAG_DONE)));
             }
         }
         return;
@@ -773,6 +846,24 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
     }
 }
 
+JSS_DEV void jss_tile_desc(const JssParams &p, int tile, int &first, int &inst, int &count) {
+    if (p.uniform_inst >= 0) {           // one instance, identity order: no descriptor loads
+        first = tile * JSS_WARPS_PER_CTA;
+        inst = p.uniform_inst;
+        count = min(JSS_WARPS_PER_CTA, p.n_envs - first);
+    } else {
+        const JssTile td = p.tiles[tile];
+        first = td.first; inst = td.inst_count >> 8; count = td.inst_count & 255;
+    }
+}
+JSS_DEV int jss_tile_env(const JssParams &p, int tile, int tile_end, int warp) {
+    if (tile >= tile_end) return -1;
+    int first, inst, count;
+    jss_tile_desc(p, tile, first, inst, count);
+    if (warp >= count) return -1;
+    return p.uniform_inst >= 0 ? first + warp : p.order[first + warp];
+}
+
 #ifndef JSS_MIN_CTAS
 #define JSS_MIN_CTAS 4   // 64 registers -> 4 CTAs = 32 warps per SM (sweep in profiles/r01_notes.md)
 #endif
@@ -781,7 +872,8 @@ template <int KJ, int MODE>
 __global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, (MODE == JSS_MODE_STEP) ? JSS_MIN_CTAS : 1)
 jss_env_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JSS_SMEM_DECL(jss_smem);
-    uint16_t *sm_ops = reinterpret_cast<uint16_t *>(jss_smem);
+    SmInst *si = reinterpret_cast<SmInst *>(jss_smem);
+    uint16_t *sm_ops = reinterpret_cast<uint16_t *>(si + 1);
     int32_t *sm_len = reinterpret_cast<int32_t *>(sm_ops + sl.ops_elems);
     uint16_t *sm_rem = reinterpret_cast<uint16_t *>(sm_len + sl.len_elems);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -790,26 +882,95 @@ jss_env_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
                           (a.rule == JSS_RULE_MWR || a.rule == JSS_RULE_LWR || a.rule == JSS_RULE_CR);
     int staged = -1;
     InstView iv;
-    iv.ops = sm_ops; iv.len = sm_len; iv.rem = sm_rem;
-    iv.J = iv.M = iv.max_time_op = iv.max_time_jobs = iv.sum_op = 0;
-    iv.f_mto = iv.f_mtj = iv.f_sop = iv.f_M = iv.r_mto = iv.r_mtj = iv.r_sop = iv.r_M = 1.0f;
+    iv.ops = sm_ops; iv.len = sm_len; iv.rem = sm_rem; iv.si = si;
+    // the masked-uniform sampler looks at no instance table at all (only J)
+    const bool want_tables = !(MODE == JSS_MODE_POLICY && a.rule == JSS_RULE_RANDOM);
     for (int tile = a.tile_begin + (int)blockIdx.x; tile < a.tile_end; tile += (int)gridDim.x) {
-        const JssTile td = p.tiles[tile];
-        const int inst = td.inst_count >> 8, count = td.inst_count & 255;
+        int first, inst, count;
+        jss_tile_desc(p, tile, first, inst, count);
         if (inst != staged) {                            // CTA-uniform
             __syncthreads();
-            const JssInstDesc d = p.inst[inst];
-            jss_stage_instance(p, d, sm_ops, sm_len, sm_rem, want_rem);
-            iv.J = d.J; iv.M = d.M; iv.max_time_op = d.max_time_op; iv.max_time_jobs = d.max_time_jobs;
-            iv.sum_op = d.sum_op;
-            iv.f_mto = (float)d.max_time_op; iv.f_mtj = (float)d.max_time_jobs; iv.f_sop = (float)d.sum_op;
-            iv.f_M = (float)d.M;
-            iv.r_mto = d.r_mto; iv.r_mtj = d.r_mtj; iv.r_sop = d.r_sop; iv.r_M = d.r_M;
+            jss_stage_instance(p, p.inst[inst], si, sm_ops, sm_len, sm_rem, want_rem, want_tables);
             staged = inst;
             __syncthreads();
         }
-        if (warp < count) jss_process_env<KJ, MODE>(p, a, iv, p.order[td.first + warp], lane, scratch);
+        if (warp < count)
+            jss_process_env<KJ, MODE>(p, a, iv, p.uniform_inst >= 0 ? first + warp : p.order[first + warp], lane,
+                                      scratch);
     }
+}
+
+// ---- the hot kernel: fused step with TMA prefetch ------------------------------------------------
+// Persistent CTAs (grid = SMs x resident CTAs), one warp per env of a tile.  Per warp in shared
+// memory: an mbarrier, a state-block buffer that receives the NEXT env's block by cp.async.bulk
+// while the current env is simulated, and the observation staging buffer that leaves by bulk store.
+template <int KJ>
+__global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, JSS_MIN_CTAS)
+jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
+    JSS_SMEM_DECL(jss_smem);
+    SmInst *si = reinterpret_cast<SmInst *>(jss_smem);
+    uint16_t *sm_ops = reinterpret_cast<uint16_t *>(si + 1);
+    int32_t *sm_len = reinterpret_cast<int32_t *>(sm_ops + sl.ops_elems);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int32_t *wbase = sm_len + sl.len_elems + (size_t)warp * (4 + sl.statein_words + sl.scratch_words);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(wbase);
+    int32_t *state_in = wbase + 4;
+    float *scratch = reinterpret_cast<float *>(state_in + sl.statein_words);
+    const uint32_t blk_bytes = (uint32_t)p.block_words * 4u;
+    if (lane == 0) jss_mbar_init(mbar);
+    __syncwarp();
+    InstView iv;
+    iv.ops = sm_ops; iv.len = sm_len; iv.rem = nullptr; iv.si = si;
+    int staged = -1;
+    uint32_t phase = 0;
+    int tile = a.tile_begin + (int)blockIdx.x;
+    int env_next = jss_tile_env(p, tile, a.tile_end, warp);
+    int act_next = 0;
+    if (env_next >= 0) {
+        if (lane == 0) jss_bulk_load(state_in, p.state + (size_t)env_next * p.block_words, blk_bytes, mbar);
+        act_next = a.actions[env_next];
+    }
+    for (; tile < a.tile_end; tile += (int)gridDim.x) {
+        int first, inst, count;
+        jss_tile_desc(p, tile, first, inst, count);
+        if (inst != staged) {                            // CTA-uniform
+            __syncthreads();
+            jss_stage_instance(p, p.inst[inst], si, sm_ops, sm_len, nullptr, false);
+            staged = inst;
+            __syncthreads();
+        }
+        const int env = env_next, action = act_next;
+        env_next = jss_tile_env(p, tile + (int)gridDim.x, a.tile_end, warp);
+        EnvRegs<KJ> s;
+        if (env >= 0) {
+            jss_mbar_wait(mbar, phase);                  // this env's block has landed in shared memory
+            phase ^= 1u;
+            env_load_from<KJ>(p, iv, state_in, lane, s);
+            __syncwarp();                                // every lane has read the buffer
+        }
+        if (env_next >= 0) {                             // prefetch the next env's block + action
+            if (lane == 0) jss_bulk_load(state_in, p.state + (size_t)env_next * p.block_words, blk_bytes, mbar);
+            act_next = a.actions[env_next];
+        }
+        if (env < 0) continue;
+        int raw = 0;
+        const uint32_t flags_in = s.flags;
+        // the previous env's observation must have left the staging buffer (also aliased by hz)
+        if (lane == 0) jss_bulk_store_wait_read();
+        __syncwarp();
+        const bool changed = env_step<KJ>(p, iv, s, env, lane, action, raw, reinterpret_cast<int *>(scratch));
+        if (changed) {
+            env_store<KJ>(p, iv, env, lane, s);
+            env_emit_all<KJ, true>(p, iv, s, env, lane, scratch, raw);
+        } else if (s.flags != flags_in) {                // only the sticky error bit changed
+            if (lane == 0) {
+                p.state[(size_t)env * p.block_words + 5 * p.Jcap + p.Mcap + 8 + JSS_HDR_FLAGS] = (int32_t)s.flags;
+                reinterpret_cast<int4 *>(p.scalars)[env] =
+                    make_int4(0, 0, s.t, (int)((s.flags << 8) | (s.flags & JSS_FLAG_DONE)));
+            }
+        }
+    }
+    if (lane == 0) jss_bulk_store_wait_all();            // shared memory must outlive the bulk reads
 }
 
 // ---- per-shard statistics ------------------------------------------------------------------

@@ -45,6 +45,7 @@ struct JssTile {       // one CTA work item: up to `count` envs of ONE instance
 struct JssParams {
     int32_t n_envs, Jcap, Mcap, block_words;
     int32_t jobs_max, machines_max, mask_stride, create_flags;
+    int32_t uniform_inst;    // >= 0: every env runs this instance and `order` is the identity
     uint64_t env_id_base;
     const JssInstDesc *inst;
     const uint16_t *ops_pool;
@@ -55,11 +56,7 @@ struct JssParams {
     int32_t *state;          // [N][block_words]
     uint8_t *mask;           // [N][mask_stride]
     float *obs;              // [N][jobs_max][7]
-    float *reward;
-    int32_t *reward_raw;
-    uint8_t *done;
-    int32_t *time;
-    uint32_t *flags;
+    int32_t *scalars;        // [N][4]: reward (f32 bits), raw reward, current_time_step, flags << 8 | done
     int32_t *solution;       // [N][jobs_max][machines_max] or nullptr
     int32_t *episode_count;
     int32_t *last_makespan;

@@ -80,11 +80,12 @@ class JssVecEnv:
         self._mask_u8 = w(b.action_mask, (n, J + 1), np.uint8, d, strides=(b.mask_stride, 1))
         self.action_mask = self._mask_u8.view(torch.bool)
         self.real_obs = w(b.real_obs, (n, J, 7), np.float32, d)
-        self.reward = w(b.reward, (n,), np.float32, d)
-        self.reward_raw = w(b.reward_raw, (n,), np.int32, d)
-        self.done = w(b.done, (n,), np.uint8, d).view(torch.bool)
-        self.current_time_step = w(b.time, (n,), np.int32, d)
-        self.flags = w(b.flags, (n,), np.int32, d)
+        ss = (int(b.scalar_stride),)      # the five scalar outputs are fields of one 16-byte record per env
+        self.reward = w(b.reward, (n,), np.float32, d, strides=ss)
+        self.reward_raw = w(b.reward_raw, (n,), np.int32, d, strides=ss)
+        self.done = w(b.done, (n,), np.uint8, d, strides=ss).view(torch.bool)
+        self.current_time_step = w(b.time, (n,), np.int32, d, strides=ss)
+        self._flags_done = w(b.flags_done, (n,), np.int32, d, strides=ss)
         self.solution = w(b.solution, (n, J, M), np.int32, d) if b.solution else None
         self.episode_count = w(b.episode_count, (n,), np.int32, d)
         self.last_makespan = w(b.last_makespan, (n,), np.int32, d)
@@ -97,6 +98,11 @@ class JssVecEnv:
         }
         self._truncated = torch.zeros(n, dtype=torch.bool, device=self.device)
         self._actions = torch.zeros(n, dtype=torch.int32, device=self.device)
+
+    @property
+    def flags(self):
+        """Per-env JSS_FLAG_* bits (done / error / no-op legal) as an int32 tensor."""
+        return self._flags_done >> 8
 
     # ---------------------------------------------------------------- lifetime
     def close(self):
@@ -203,7 +209,7 @@ class JssVecEnv:
         N.check(self._h, self._L.jss_export_state(self._h, self._stream()), "jss_export_state")
         d = dict(self._x)
         d["t"] = self.current_time_step
-        d["flags"] = self.flags
+        d["flags"] = self._flags_done
         return d
 
     def import_state(self, state: Dict[str, Any], mask=None):
@@ -213,8 +219,8 @@ class JssVecEnv:
                 dst.copy_(state[k])
         if state["t"].data_ptr() != self.current_time_step.data_ptr():
             self.current_time_step.copy_(state["t"])
-        if state["flags"].data_ptr() != self.flags.data_ptr():
-            self.flags.copy_(state["flags"])
+        if state["flags"].data_ptr() != self._flags_done.data_ptr():
+            self._flags_done.copy_(state["flags"])
         ptr = None
         if mask is not None:
             import torch

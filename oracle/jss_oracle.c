@@ -33,9 +33,11 @@
  *   JSSO_ERR_EMPTY_QUEUE  list.pop(0) on an empty event list (jss_env.py:517)
  *   JSSO_ERR_JOB_FINISHED instance_matrix[action][M] IndexError (jss_env.py:444)
  */
+#define _POSIX_C_SOURCE 200809L
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #define JSSO_OK 0
 #define JSSO_ERR_EMPTY_QUEUE (-1)
@@ -563,6 +565,33 @@ int64_t jsso_run_random(jsso *o, uint64_t seed, uint64_t env, int64_t n_steps,
             *sum_makespan += o->current_time_step;
             jsso_reset(o);
         }
+    }
+    return steps;
+}
+
+/* Same driver, bounded by wall time instead of a step count (bench.py's CPU legs run one
+ * of these per host thread for a fixed window).  Returns the steps executed. */
+int64_t jsso_run_random_timed(jsso *o, uint64_t seed, uint64_t env, double seconds,
+                              int64_t *episodes, int64_t *sum_makespan) {
+    struct timespec t0, t1;
+    int64_t steps = 0, ctr = 0;
+    double r; int64_t raw; int done = 0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    jsso_reset(o);
+    for (;;) {
+        for (int k = 0; k < 512; k++) {
+            int a = jsso_masked_random_action(o, seed, env, (uint64_t)ctr);
+            ctr++;
+            if (a < 0 || jsso_step(o, a, &r, &raw, &done) != JSSO_OK) return -1;
+            steps++;
+            if (done) {
+                *episodes += 1;
+                *sum_makespan += o->current_time_step;
+                jsso_reset(o);
+            }
+        }
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        if ((double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec) >= seconds) break;
     }
     return steps;
 }

@@ -46,6 +46,9 @@ def lib():
         L.jsso_run_random.restype = ctypes.c_int64
         L.jsso_run_random.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int64,
                                       ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+        L.jsso_run_random_timed.restype = ctypes.c_int64
+        L.jsso_run_random_timed.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_double,
+                                            ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
         _lib = L
     return _lib
 
@@ -166,4 +169,9 @@ class OracleEnv:
     def run_random(self, seed: int, env: int, n_steps: int):
         ep, ms = ctypes.c_int64(0), ctypes.c_int64(0)
         n = self._L.jsso_run_random(self._h, seed, env, n_steps, ctypes.byref(ep), ctypes.byref(ms))
+        return int(n), int(ep.value), int(ms.value)
+
+    def run_random_timed(self, seed: int, env: int, seconds: float):
+        ep, ms = ctypes.c_int64(0), ctypes.c_int64(0)
+        n = self._L.jsso_run_random_timed(self._h, seed, env, float(seconds), ctypes.byref(ep), ctypes.byref(ms))
         return int(n), int(ep.value), int(ms.value)

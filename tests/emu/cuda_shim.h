@@ -73,6 +73,7 @@ static inline unsigned __reduce_or_sync(unsigned mask, unsigned v) { return (uns
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::collective(emu::OP_SYNCWARP, mask, 0, 0); }
 static inline void __syncthreads() { emu::collective(emu::OP_SYNCTHREADS, 0xffffffffu, 0, 0); }
 
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline float __fdiv_rn(float a, float b) { return a / b; }  // IEEE fp32 divide, round-to-nearest
@@ -124,5 +125,8 @@ static inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, s
 }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename F>
+static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
 template <typename F>
 static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 1; return 0; }
