@@ -174,17 +174,25 @@ int jss_step(jss_t *h, const int32_t *actions_dev, void *stream);
 int jss_policy(jss_t *h, int rule, int coin_mode, uint64_t seed, uint64_t step_index,
                int32_t *actions_dev, void *stream);
 
+/* jss_step() fused with jss_policy() for the NEXT decision: applies actions_dev, then
+ * writes every env's next action (chosen by `rule` on the new state, RNG counter
+ * `step_index`) to next_actions_dev, in one launch.  The two buffers may alias. */
+int jss_step_sample(jss_t *h, const int32_t *actions_dev, int rule, int coin_mode, uint64_t seed,
+                    uint64_t step_index, int32_t *next_actions_dev, void *stream);
+
 /* Replaces DispatchingRule.run_episode (dispatching.py:55-75) for the whole
  * batch: n_steps x (policy -> step) fused in one launch, state kept on chip
  * between steps; observations are written every step iff write_obs != 0. */
 int jss_rollout(jss_t *h, int rule, uint64_t seed, uint64_t step_index, int n_steps,
                 int write_obs, void *stream);
 
-/* Host-buffer form of step(): copies actions H2D, steps, copies the
- * observation D2H, synchronises.  Any output pointer may be NULL.  Host rows
- * are dense: mask [N][J+1], obs [N][J][7]. */
+/* Host-buffer form of step(): copies actions H2D, steps, copies the results D2H with
+ * contiguous DMA, synchronises.  Any output pointer may be NULL.  Host layouts equal the
+ * device layouts: mask_host [N][mask_stride] bytes (row i: bytes 0..J_i), obs_host
+ * [N][J][7] fp32, scalars_host [N][4] int32 = the 16-byte records
+ * {reward (fp32 bits), reward_raw, current_time_step, flags << 8 | done}. */
 int jss_step_host(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, float *obs_host,
-                  float *reward_host, uint8_t *done_host, void *stream);
+                  int32_t *scalars_host, void *stream);
 
 /* --- auxiliary ----------------------------------------------------------- */
 
@@ -197,8 +205,9 @@ int jss_export_state(jss_t *h, void *stream);
 int jss_import_state(jss_t *h, const uint8_t *env_mask_dev, void *stream);
 
 /* Host utility with the device policy's RNG: masked-uniform action per env from
- * a dense host mask [n][width] (width = J+1), for host-side agents and tests. */
-int jss_host_masked_random(const uint8_t *mask_host, int n, int width, uint64_t seed,
+ * a host mask of n rows of `width` (= J+1) bytes, `row_stride` bytes apart, for
+ * host-side agents and tests (multi-threaded for large batches). */
+int jss_host_masked_random(const uint8_t *mask_host, int n, int width, int64_t row_stride, uint64_t seed,
                            uint64_t env_id_base, uint64_t step_index, int32_t *actions_host);
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */

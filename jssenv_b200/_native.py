@@ -25,7 +25,7 @@ STATS_KEYS = ("episodes", "steps", "sum_makespan", "min_makespan", "max_makespan
 EXPORTED_SYMBOLS = (
     "jss_abi_version", "jss_create", "jss_destroy", "jss_last_error", "jss_load_instances", "jss_assign",
     "jss_get_buffers", "jss_instance_scalars", "jss_reset", "jss_step", "jss_policy", "jss_rollout",
-    "jss_step_host", "jss_stats", "jss_export_state", "jss_import_state", "jss_host_masked_random",
+    "jss_step_host", "jss_step_sample", "jss_stats", "jss_export_state", "jss_import_state", "jss_host_masked_random",
     "jss_launch_count",
 )
 
@@ -61,16 +61,17 @@ def _declare(L):
     L.jss_reset.argtypes = [c_void_p, c_void_p, c_void_p]
     L.jss_step.argtypes = [c_void_p, c_void_p, c_void_p]
     L.jss_policy.argtypes = [c_void_p, c_int, c_int, c_uint64, c_uint64, c_void_p, c_void_p]
+    L.jss_step_sample.argtypes = [c_void_p, c_void_p, c_int, c_int, c_uint64, c_uint64, c_void_p, c_void_p]
     L.jss_rollout.argtypes = [c_void_p, c_int, c_uint64, c_uint64, c_int, c_int, c_void_p]
-    L.jss_step_host.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.jss_step_host.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.jss_stats.argtypes = [c_void_p, POINTER(c_int64), c_void_p]
     L.jss_export_state.argtypes = [c_void_p, c_void_p]
     L.jss_import_state.argtypes = [c_void_p, c_void_p, c_void_p]
-    L.jss_host_masked_random.argtypes = [c_void_p, c_int, c_int, c_uint64, c_uint64, c_uint64, c_void_p]
+    L.jss_host_masked_random.argtypes = [c_void_p, c_int, c_int, c_int64, c_uint64, c_uint64, c_uint64, c_void_p]
     L.jss_launch_count.argtypes = [c_void_p]
     L.jss_launch_count.restype = c_int64
     for name in ("jss_create", "jss_load_instances", "jss_assign", "jss_get_buffers", "jss_instance_scalars",
-                 "jss_reset", "jss_step", "jss_policy", "jss_rollout", "jss_step_host", "jss_stats",
+                 "jss_reset", "jss_step", "jss_policy", "jss_rollout", "jss_step_host", "jss_step_sample", "jss_stats",
                  "jss_export_state", "jss_import_state", "jss_host_masked_random"):
         getattr(L, name).restype = c_int
     return L

@@ -55,7 +55,7 @@ struct jss_handle {
     JssParams p{};
     JssSmemLayout sl_norem{}, sl_rem{};
     int class_tile_begin[3] = {0, 0, 0}, class_tile_end[3] = {0, 0, 0};  // KJ = 1, 2, 4
-    int step_grid[3] = {0, 0, 0};
+    int step_grid[12] = {0};
     std::vector<int32_t> env_inst;
 
     // pinned staging for jss_step_host
@@ -103,18 +103,18 @@ size_t smem_bytes(const JssSmemLayout &sl) {
            (size_t)JSS_WARPS_PER_CTA * sl.scratch_words * 4;
 }
 size_t smem_bytes_step(const JssSmemLayout &sl) {
-    return sizeof(SmInst) + (size_t)sl.ops_elems * 2 + (size_t)sl.len_elems * 4 +
+    return sizeof(SmInst) + (size_t)sl.ops_elems * 2 + (size_t)sl.len_elems * 4 + (size_t)sl.rem_elems * 2 +
            (size_t)JSS_WARPS_PER_CTA * (4 + sl.statein_words + sl.scratch_words) * 4;
 }
 
-template <int KJ>
-int launch_step(jss_t *h, const JssLaunch &a, cudaStream_t st) {
+template <int KJ, bool SAMPLE>
+int launch_step_variant(jss_t *h, const JssLaunch &a, bool want_rem, cudaStream_t st) {
     const int n_tiles = a.tile_end - a.tile_begin;
-    JssSmemLayout sl = h->sl_norem;
+    JssSmemLayout sl = want_rem ? h->sl_rem : h->sl_norem;
     sl.statein_words = h->p.block_words;
     const size_t smem = smem_bytes_step(sl);
-    auto kern = jss_step_kernel<KJ>;
-    int &grid = h->step_grid[KJ == 1 ? 0 : (KJ == 2 ? 1 : 2)];
+    auto kern = jss_step_kernel<KJ, SAMPLE>;
+    int &grid = h->step_grid[(KJ == 1 ? 0 : (KJ == 2 ? 1 : 2)) * 4 + (SAMPLE ? 2 : 0) + (want_rem ? 1 : 0)];
     if (grid == 0) {                                     // once per handle: opt-in smem + occupancy
         if (smem > 48 * 1024)
             JSS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -129,6 +129,12 @@ int launch_step(jss_t *h, const JssLaunch &a, cudaStream_t st) {
     return JSS_OK;
 }
 
+template <int KJ>
+int launch_step(jss_t *h, const JssLaunch &a, cudaStream_t st) {
+    if (a.actions_out == nullptr) return launch_step_variant<KJ, false>(h, a, false, st);
+    return launch_step_variant<KJ, true>(h, a, a.rule == JSS_RULE_MWR || a.rule == JSS_RULE_LWR || a.rule == JSS_RULE_CR, st);
+}
+
 template <int KJ, int MODE>
 int launch_variant(jss_t *h, const JssLaunch &a, const JssSmemLayout &sl, cudaStream_t st) {
     const int n_tiles = a.tile_end - a.tile_begin;
@@ -137,7 +143,9 @@ int launch_variant(jss_t *h, const JssLaunch &a, const JssSmemLayout &sl, cudaSt
     int per_sm = 0;
     JSS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, JSS_WARPS_PER_CTA * 32, smem));
     if (per_sm < 1) return fail(h, JSS_ERR_CUDA, "kernel does not fit on an SM (smem %zu B)", smem);
-    const int grid = std::min(n_tiles, h->sm_count * per_sm);
+    // policy kernels touch ~50 B per env: latency-bound, so give every tile its own CTA
+    // instead of a persistent loop with a dependent load per iteration
+    const int grid = (MODE == JSS_MODE_POLICY) ? n_tiles : std::min(n_tiles, h->sm_count * per_sm);
     JSS_LAUNCH(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl);
     JSS_CUDA(h, cudaGetLastError());
     h->launches += 1;
@@ -465,6 +473,21 @@ int jss_step(jss_t *h, const int32_t *actions_dev, void *stream) {
     return launch_all(h, a, false, (cudaStream_t)stream);
 }
 
+int jss_step_sample(jss_t *h, const int32_t *actions_dev, int rule, int coin_mode, uint64_t seed,
+                    uint64_t step_index, int32_t *next_actions_dev, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!actions_dev || !next_actions_dev || rule < 0 || rule >= JSS_NUM_RULES ||
+        (coin_mode != JSS_COIN_DEVICE && coin_mode != JSS_COIN_NEVER))
+        return fail(h, JSS_ERR_INVALID, "jss_step_sample: bad arguments (rule %d, coin %d)", rule, coin_mode);
+    JssLaunch a{};
+    a.mode = JSS_MODE_STEP;
+    a.actions = actions_dev;
+    a.actions_out = next_actions_dev;
+    a.rule = rule; a.coin_mode = coin_mode; a.seed = seed; a.step_index = step_index;
+    return launch_all(h, a, false, (cudaStream_t)stream);
+}
+
 int jss_policy(jss_t *h, int rule, int coin_mode, uint64_t seed, uint64_t step_index, int32_t *actions_dev,
                void *stream) {
     int rc = check_ready(h);
@@ -490,8 +513,8 @@ int jss_rollout(jss_t *h, int rule, uint64_t seed, uint64_t step_index, int n_st
     return launch_all(h, a, rule_wants_rem(rule), (cudaStream_t)stream);
 }
 
-int jss_step_host(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, float *obs_host, float *reward_host,
-                  uint8_t *done_host, void *stream) {
+int jss_step_host(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, float *obs_host,
+                  int32_t *scalars_host, void *stream) {
     int rc = check_ready(h);
     if (rc) return rc;
     if (!actions_host) return fail(h, JSS_ERR_INVALID, "jss_step_host: actions_host is NULL");
@@ -501,15 +524,13 @@ int jss_step_host(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, flo
     JSS_CUDA(h, cudaMemcpyAsync(h->dev_actions, actions_host, N * 4, cudaMemcpyHostToDevice, st));
     rc = jss_step(h, h->dev_actions, stream);
     if (rc) return rc;
+    // contiguous DMA only: host rows keep the device pitches (mask rows: mask_stride bytes,
+    // scalar records: 16 bytes) -- pitched 2-D copies of 65 536 tiny rows are several times slower
     if (mask_host)
-        JSS_CUDA(h, cudaMemcpy2DAsync(mask_host, (size_t)p.jobs_max + 1, p.mask, (size_t)p.mask_stride,
-                                      (size_t)p.jobs_max + 1, N, cudaMemcpyDeviceToHost, st));
+        JSS_CUDA(h, cudaMemcpyAsync(mask_host, p.mask, N * p.mask_stride, cudaMemcpyDeviceToHost, st));
     if (obs_host)
         JSS_CUDA(h, cudaMemcpyAsync(obs_host, p.obs, N * p.jobs_max * 7 * 4, cudaMemcpyDeviceToHost, st));
-    if (reward_host)
-        JSS_CUDA(h, cudaMemcpy2DAsync(reward_host, 4, p.scalars, 16, 4, N, cudaMemcpyDeviceToHost, st));
-    if (done_host)
-        JSS_CUDA(h, cudaMemcpy2DAsync(done_host, 1, p.scalars + 3, 16, 1, N, cudaMemcpyDeviceToHost, st));
+    if (scalars_host) JSS_CUDA(h, cudaMemcpyAsync(scalars_host, p.scalars, N * 16, cudaMemcpyDeviceToHost, st));
     JSS_CUDA(h, cudaStreamSynchronize(st));
     return JSS_OK;
 }
@@ -551,12 +572,12 @@ int jss_import_state(jss_t *h, const uint8_t *env_mask_dev, void *stream) {
     return launch_all(h, a, false, (cudaStream_t)stream);
 }
 
-int jss_host_masked_random(const uint8_t *mask_host, int n, int width, uint64_t seed, uint64_t env_id_base,
-                           uint64_t step_index, int32_t *actions_host) {
-    if (!mask_host || !actions_host || n < 0 || width <= 0) return JSS_ERR_INVALID;
+int jss_host_masked_random(const uint8_t *mask_host, int n, int width, int64_t row_stride, uint64_t seed,
+                           uint64_t env_id_base, uint64_t step_index, int32_t *actions_host) {
+    if (!mask_host || !actions_host || n < 0 || width <= 0 || row_stride < width) return JSS_ERR_INVALID;
     auto work = [&](int lo, int hi) {
         for (int e = lo; e < hi; e++) {
-            const uint8_t *row = mask_host + (size_t)e * width;
+            const uint8_t *row = mask_host + (size_t)e * (size_t)row_stride;
             int cnt = 0;
             for (int i = 0; i < width; i++) cnt += row[i] != 0;
             int act = JSS_ACTION_SKIP;

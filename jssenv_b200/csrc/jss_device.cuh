@@ -904,7 +904,9 @@ jss_env_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
 // Persistent CTAs (grid = SMs x resident CTAs), one warp per env of a tile.  Per warp in shared
 // memory: an mbarrier, a state-block buffer that receives the NEXT env's block by cp.async.bulk
 // while the current env is simulated, and the observation staging buffer that leaves by bulk store.
-template <int KJ>
+// SAMPLE = true additionally picks every env's NEXT action (masked-uniform sampler or a
+// dispatching rule) from the freshly computed state, so a policy-driven loop is one launch per step.
+template <int KJ, bool SAMPLE>
 __global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, JSS_MIN_CTAS)
 jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JSS_SMEM_DECL(jss_smem);
@@ -912,7 +914,9 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     uint16_t *sm_ops = reinterpret_cast<uint16_t *>(si + 1);
     int32_t *sm_len = reinterpret_cast<int32_t *>(sm_ops + sl.ops_elems);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int32_t *wbase = sm_len + sl.len_elems + (size_t)warp * (4 + sl.statein_words + sl.scratch_words);
+    uint16_t *sm_rem = reinterpret_cast<uint16_t *>(sm_len + sl.len_elems);
+    int32_t *wbase = reinterpret_cast<int32_t *>(sm_rem + sl.rem_elems) +
+                     (size_t)warp * (4 + sl.statein_words + sl.scratch_words);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(wbase);
     int32_t *state_in = wbase + 4;
     float *scratch = reinterpret_cast<float *>(state_in + sl.statein_words);
@@ -920,7 +924,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     if (lane == 0) jss_mbar_init(mbar);
     __syncwarp();
     InstView iv;
-    iv.ops = sm_ops; iv.len = sm_len; iv.rem = nullptr; iv.si = si;
+    iv.ops = sm_ops; iv.len = sm_len; iv.rem = sm_rem; iv.si = si;
     int staged = -1;
     uint32_t phase = 0;
     int tile = a.tile_begin + (int)blockIdx.x;
@@ -935,7 +939,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
         jss_tile_desc(p, tile, first, inst, count);
         if (inst != staged) {                            // CTA-uniform
             __syncthreads();
-            jss_stage_instance(p, p.inst[inst], si, sm_ops, sm_len, nullptr, false);
+            jss_stage_instance(p, p.inst[inst], si, sm_ops, sm_len, sm_rem, SAMPLE && sl.rem_elems > 0);
             staged = inst;
             __syncthreads();
         }
@@ -959,6 +963,11 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
         if (lane == 0) jss_bulk_store_wait_read();
         __syncwarp();
         const bool changed = env_step<KJ>(p, iv, s, env, lane, action, raw, reinterpret_cast<int *>(scratch));
+        if (SAMPLE) {
+            const uint32_t h = jss_hash3(a.seed, p.env_id_base + (uint64_t)env, a.step_index);
+            const int nxt = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h);
+            if (lane == 0) a.actions_out[env] = nxt;
+        }
         if (changed) {
             env_store<KJ>(p, iv, env, lane, s);
             env_emit_all<KJ, true>(p, iv, s, env, lane, scratch, raw);

@@ -142,6 +142,22 @@ class JssVecEnv:
         N.check(self._h, self._L.jss_step(self._h, ctypes.c_void_p(a.data_ptr()), self._stream()), "jss_step")
         return self._obs(), self.reward, self.done, self._truncated, {}
 
+    def step_sample(self, actions, rule: Union[str, int] = "RANDOM", coin: str = "device", out=None):
+        """step(actions) fused with policy(rule) for the next decision (one launch): returns the usual
+        step tuple plus the int32[N] tensor of next actions (`out`, default: in place of `actions`)."""
+        import torch
+        a = torch.as_tensor(actions, device=self.device)
+        if a.dtype != torch.int32 or not a.is_contiguous():
+            a = a.to(torch.int32).contiguous()
+        out = a if out is None else out
+        r = N.RULES[rule.upper()] if isinstance(rule, str) else int(rule)
+        rc = self._L.jss_step_sample(self._h, ctypes.c_void_p(a.data_ptr()), r,
+                                     N.COIN_DEVICE if coin == "device" else N.COIN_NEVER, self.seed,
+                                     self._step_index, ctypes.c_void_p(out.data_ptr()), self._stream())
+        N.check(self._h, rc, "jss_step_sample")
+        self._step_index += 1
+        return self._obs(), self.reward, self.done, self._truncated, {}, out
+
     def get_legal_actions(self):
         return self.action_mask
 
@@ -176,22 +192,30 @@ class JssVecEnv:
             import torch
             pin = N.backend.name == "cuda"
             mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin)   # noqa: E731
-            self._host = {"mask": mk((n, J + 1), torch.uint8), "obs": mk((n, J, 7), torch.float32),
-                          "reward": mk((n,), torch.float32), "done": mk((n,), torch.uint8)}
-        hb = self._host
+            ms = int(self._b.mask_stride)
+            self._host = {"mask": mk((n, ms), torch.uint8), "obs": mk((n, J, 7), torch.float32),
+                          "scalars": mk((n, 4), torch.int32)}
+            sc = self._host["scalars"].numpy()
+            self._host_views = {
+                "mask": self._host["mask"].numpy()[:, : J + 1].view(np.bool_), "obs": self._host["obs"].numpy(),
+                "reward": sc.view(np.float32)[:, 0], "done": sc.view(np.uint8)[:, 12].view(np.bool_)}
+        hb, hv = self._host, self._host_views
         rc = self._L.jss_step_host(self._h, ctypes.c_void_p(a.ctypes.data), ctypes.c_void_p(hb["mask"].data_ptr()),
                                    ctypes.c_void_p(hb["obs"].data_ptr()) if want_obs else None,
-                                   ctypes.c_void_p(hb["reward"].data_ptr()), ctypes.c_void_p(hb["done"].data_ptr()),
-                                   self._stream())
+                                   ctypes.c_void_p(hb["scalars"].data_ptr()), self._stream())
         N.check(self._h, rc, "jss_step_host")
-        obs = {"real_obs": hb["obs"].numpy(), "action_mask": hb["mask"].numpy().view(np.bool_)}
-        return obs, hb["reward"].numpy(), hb["done"].numpy().view(np.bool_), np.zeros(n, np.bool_), {}
+        obs = {"real_obs": hv["obs"], "action_mask": hv["mask"]}
+        return obs, hv["reward"], hv["done"], np.zeros(n, np.bool_), {}
 
     def host_masked_random(self, mask: np.ndarray, step_index: int) -> np.ndarray:
         """Same draw as policy('RANDOM') but from a host mask (for host-side agents / tests)."""
-        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        m = np.asarray(mask)
+        if m.dtype != np.uint8:
+            m = m.view(np.uint8) if m.dtype == np.bool_ else m.astype(np.uint8)
+        if m.strides[1] != 1:
+            m = np.ascontiguousarray(m)
         out = np.empty(m.shape[0], np.int32)
-        rc = self._L.jss_host_masked_random(ctypes.c_void_p(m.ctypes.data), m.shape[0], m.shape[1], self.seed,
+        rc = self._L.jss_host_masked_random(ctypes.c_void_p(m.ctypes.data), m.shape[0], m.shape[1], m.strides[0], self.seed,
                                             self.env_id_base, int(step_index), ctypes.c_void_p(out.ctypes.data))
         if rc != 0:
             raise N.NativeError("jss_host_masked_random failed")

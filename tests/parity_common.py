@@ -396,3 +396,23 @@ def check_step_host(make_env, name, seed):
         assert np.array_equal(rew, _np(ref.reward)) and np.array_equal(done, _np(ref.done))
         mask = obs["action_mask"]
     return env
+
+
+def check_step_sample(make_env, names, rule, n_steps, seed):
+    """jss_step_sample (step fused with the next decision) == policy kernel + step kernel."""
+    uniq = sorted(set(names))
+    cfg = {"instance_paths": uniq, "env_to_instance": [uniq.index(n) for n in names]}
+    a_env = make_env(len(names), cfg, seed=seed, auto_reset=True)
+    b_env = make_env(len(names), cfg, seed=seed, auto_reset=True)
+    a_env.reset(); b_env.reset()
+    act_a = a_env.policy(rule).clone()             # step_index 0
+    b_env._step_index = 0
+    for k in range(n_steps):
+        act_b = b_env.policy(rule)                 # step_index k
+        assert np.array_equal(_np(act_a), _np(act_b)), f"actions differ at step {k}"
+        b_env.step(act_b)
+        *_, act_a = a_env.step_sample(act_a, rule)  # applies step k, samples with step_index k+1
+        for name in ("action_mask", "real_obs", "reward", "reward_raw", "done", "current_time_step"):
+            assert np.array_equal(_np(getattr(a_env, name)), _np(getattr(b_env, name))), (k, name)
+    assert a_env.stats() == b_env.stats()
+    return a_env

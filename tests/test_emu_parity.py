@@ -80,3 +80,8 @@ def test_emu_snapshot_restore():
 
 def test_emu_step_host():
     pc.check_step_host(make_env, "ta01", seed=1)
+
+
+@pytest.mark.parametrize("rule", ["RANDOM", "MWR"])
+def test_emu_step_sample_fused(rule):
+    pc.check_step_sample(make_env, ["ta01", "ta51", "ta80"], rule, n_steps=300, seed=12)
