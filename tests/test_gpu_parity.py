@@ -157,3 +157,59 @@ def test_gpu_large_batch_invariants():
             _, _, done, _, _ = o.step(o.masked_random_action(99, i, step))
             step += 1
         assert int(mk[i]) == o.current_time_step
+
+
+def test_gpu_config2_ta01_n4096_random():
+    """BASELINE.json configs[1]: ta01 N = 4096, masked-random policy; every 256th env replayed by the oracle."""
+    from jssenv_b200.instances import load_instance
+    from oracle.jss_oracle import OracleEnv
+    n = 4096
+    env = make_env(n, {"instance_path": "ta01"}, seed=31)
+    env.reset()
+    acts = env.policy("RANDOM").clone()
+    for _ in range(400):
+        *_, acts = env.step_sample(acts, "RANDOM")
+    st = env.stats()
+    assert st["envs_done"] == n and st["envs_error"] == 0 and st["episodes"] == n
+    mk = env.last_makespan.cpu().numpy()
+    ret = env.last_return.cpu().numpy()
+    sum_op = int(env.instance_scalars[0, 2])
+    assert (ret == 2 * sum_op - 15 * mk).all()
+    for i in range(0, n, 256):
+        o = OracleEnv(*load_instance("ta01"))
+        o.reset()
+        done, step = False, 0
+        while not done:
+            _, _, done, _, _ = o.step(o.masked_random_action(31, i, step))
+            step += 1
+        assert mk[i] == o.current_time_step, i
+
+
+def test_gpu_config5_mixed_ta01_ta80_rules():
+    """BASELINE.json configs[4]: env i runs ta{(i mod 80)+1}, N = 65 536, on-device FIFO and MWR
+    (fused rollouts, device coin).  Episode identity for all envs, oracle replay for a sample."""
+    import torch
+    from jssenv_b200.dispatching import get_rule
+    from jssenv_b200.instances import load_instance
+    from oracle.jss_oracle import OracleEnv
+    names = ["ta%02d" % (k + 1) for k in range(80)]
+    n = 65536
+    env = make_env(n, {"instance_paths": names, "env_to_instance": np.arange(n) % 80}, seed=77)
+    sc = env.instance_scalars[env.env_to_instance]
+    sum_op = torch.as_tensor(sc[:, 2], device=env.device)
+    M = torch.as_tensor(env.env_machines.astype(np.int64), device=env.device)
+    for rule in ("FIFO", "MWR"):
+        base = env._step_index
+        ret, mk = get_rule(rule).run_batch(env)
+        st = env.stats()
+        assert st["envs_done"] == n and st["envs_error"] == 0
+        assert bool((ret.long() == 2 * sum_op - M * mk.long()).all()), rule
+        for i in (0, 1, 14, 40, 79, 80 * 400 + 50, n - 1):
+            o = OracleEnv(*load_instance(names[i % 80]))
+            o.reset()
+            done, step = False, 0
+            while not done:
+                a, _ = o.rule_action(rule, pc._coin_uniform(77, i, base + step))
+                _, _, done, _, _ = o.step(a)
+                step += 1
+            assert int(mk[i]) == o.current_time_step, (rule, i)
