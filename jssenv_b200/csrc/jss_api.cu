@@ -107,14 +107,14 @@ size_t smem_bytes_step(const JssSmemLayout &sl) {
            (size_t)JSS_WARPS_PER_CTA * (4 + sl.statein_words + sl.scratch_words) * 4;
 }
 
-template <int KJ, bool SAMPLE>
+template <int KJ, int SAMPLE>
 int launch_step_variant(jss_t *h, const JssLaunch &a, bool want_rem, cudaStream_t st) {
     const int n_tiles = a.tile_end - a.tile_begin;
     JssSmemLayout sl = want_rem ? h->sl_rem : h->sl_norem;
     sl.statein_words = h->p.block_words;
     const size_t smem = smem_bytes_step(sl);
     auto kern = jss_step_kernel<KJ, SAMPLE>;
-    int &grid = h->step_grid[(KJ == 1 ? 0 : (KJ == 2 ? 1 : 2)) * 4 + (SAMPLE ? 2 : 0) + (want_rem ? 1 : 0)];
+    int &grid = h->step_grid[(KJ == 1 ? 0 : (KJ == 2 ? 1 : 2)) * 4 + SAMPLE + (want_rem ? 1 : 0)];
     if (grid == 0) {                                     // once per handle: opt-in smem + occupancy
         if (smem > 48 * 1024)
             JSS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -131,8 +131,9 @@ int launch_step_variant(jss_t *h, const JssLaunch &a, bool want_rem, cudaStream_
 
 template <int KJ>
 int launch_step(jss_t *h, const JssLaunch &a, cudaStream_t st) {
-    if (a.actions_out == nullptr) return launch_step_variant<KJ, false>(h, a, false, st);
-    return launch_step_variant<KJ, true>(h, a, a.rule == JSS_RULE_MWR || a.rule == JSS_RULE_LWR || a.rule == JSS_RULE_CR, st);
+    if (a.actions_out == nullptr) return launch_step_variant<KJ, 0>(h, a, false, st);
+    if (a.rule == JSS_RULE_RANDOM) return launch_step_variant<KJ, 1>(h, a, false, st);
+    return launch_step_variant<KJ, 2>(h, a, a.rule == JSS_RULE_MWR || a.rule == JSS_RULE_LWR || a.rule == JSS_RULE_CR, st);
 }
 
 template <int KJ, int MODE>

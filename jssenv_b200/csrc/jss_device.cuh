@@ -326,12 +326,17 @@ JSS_DEV uint32_t env_machine_legal(const EnvRegs<KJ> &s) {
 // ---- _prioritization_non_final (jss_env.py:183-254) --------------------------------
 template <int KJ>
 JSS_DEV void env_prioritize(const InstView &iv, EnvRegs<KJ> &s, int lane) {
-    uint32_t fin = 0u, fin_m = 0u;                        // my legal FINAL ops / their machines
+    uint32_t fin = 0u;                                    // my legal FINAL ops
+    const int last = iv.si->M - 1;
+#pragma unroll
+    for (int i = 0; i < KJ; i++) fin |= (s.todo[i] == last ? 1u : 0u) << i;
+    fin &= s.lb;
+    if (!__any_sync(JSS_FULL, fin != 0u)) return;         // nothing can be de-legalised (the common case)
+    uint32_t fin_m = 0u;                                  // machines wanted by a legal final op
 #pragma unroll
     for (int i = 0; i < KJ; i++)
-        if ((s.lb & (1u << i)) && s.todo[i] == iv.si->M - 1) { fin |= 1u << i; fin_m |= 1u << (jss_op_m(s.op[i]) & 31u); }
+        if (fin & (1u << i)) fin_m |= 1u << (jss_op_m(s.op[i]) & 31u);
     fin_m = __reduce_or_sync(JSS_FULL, fin_m);
-    if (fin_m == 0u) return;                              // nothing can be de-legalised
     const uint32_t free_m = __ballot_sync(JSS_FULL, lane < iv.si->M && s.tuam == 0);
     int cand_d[KJ];                                       // duration if legal non-final op whose NEXT machine is free
     const int row = KJ * lane * iv.si->M;
@@ -487,9 +492,8 @@ JSS_DEV void env_emit_mask(const JssParams &p, const InstView &iv, const EnvRegs
     const int j0 = KJ * lane;
     if (j0 <= iv.si->J) {
         // spread the legal bits to bytes: bit i -> byte i
-        uint32_t w = 0u;
-#pragma unroll
-        for (int i = 0; i < KJ; i++) w |= ((s.lb >> i) & 1u) << (8 * i);
+        // bit i -> byte i: the products of the set bits land on distinct positions (no carries)
+        uint32_t w = ((s.lb & jss_legal_mask<KJ>()) * 0x00204081u) & 0x01010101u;
         if (iv.si->J - j0 < KJ) w |= (noop ? 1u : 0u) << (8 * (iv.si->J - j0));     // byte J is the no-op flag
         if (KJ == 4) *reinterpret_cast<uint32_t *>(row + j0) = w;
         else if (KJ == 2) *reinterpret_cast<uint16_t *>(row + j0) = (uint16_t)w;
@@ -549,21 +553,12 @@ JSS_DEV bool env_step(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, in
         return false;  // frozen until reset
     }
     constexpr uint32_t LM = jss_legal_mask<KJ>();
-    int holes = 0;
-    if (action == JSS_ACTION_ADVANCE || action == iv.si->J) {
+    int holes = 0, gain = 0;
+    const bool wait = (action == JSS_ACTION_ADVANCE || action == iv.si->J);
+    if (wait) {
         if (!__any_sync(JSS_FULL, s.tuam > 0)) { s.flags |= JSS_FLAG_ERROR; return false; }   // IndexError at :517
-        if (action == JSS_ACTION_ADVANCE) {              // raw increase_time_step()
-            raw_reward = -env_advance<KJ>(iv, s, lane);
-            return true;                                 // the heuristics and _is_done do NOT run here
-        }
-        s.lb = (s.lb & ~LM) | ((s.lb & LM) << 4) | (s.lb & (LM << 4));   // no-op (:419-428): legal -> blocked
-        bool none;
-        do {                                             // :429-430
-            holes += env_advance<KJ>(iv, s, lane);
-            none = !__any_sync(JSS_FULL, (s.lb & LM) != 0u);
-        } while (none && __any_sync(JSS_FULL, s.tuam > 0));
-        if (none) s.flags |= JSS_FLAG_ERROR;             // the reference raises here (empty queue)
-        raw_reward = -holes;
+        if (action == iv.si->J)                          // no-op (:419-428): legal -> blocked
+            s.lb = ((s.lb & LM) << 4) | (s.lb & (LM << 4));
     } else {                                             // job allocation (:441-481)
         if (action < 0 || action > iv.si->J) { s.flags |= JSS_FLAG_ERROR; return false; }
         const int la = action / KJ, ia = action % KJ;
@@ -571,11 +566,11 @@ JSS_DEV bool env_step(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, in
         const uint32_t bits_a = __shfl_sync(JSS_FULL, s.lb, la);
         if (opa == JSS_OP_NONE || !((bits_a >> ia) & 1u)) { s.flags |= JSS_FLAG_ERROR; return false; }
         const uint32_t m_a = jss_op_m(opa);
-        const int d_a = jss_op_d(opa);
-        if ((uint32_t)lane == m_a) s.tuam = d_a;                     // :446
+        gain = jss_op_d(opa);
+        if ((uint32_t)lane == m_a) s.tuam = gain;                    // :446
         if (lane == la) {
 #pragma unroll
-            for (int i = 0; i < KJ; i++) if (i == ia) s.tufco[i] = d_a;   // :447
+            for (int i = 0; i < KJ; i++) if (i == ia) s.tufco[i] = gain;   // :447
             if (p.solution)                                           // :454
                 p.solution[((size_t)env * p.jobs_max + action) * p.machines_max + jss_sel<KJ>(s.todo, ia)] = s.t;
         }
@@ -584,10 +579,18 @@ JSS_DEV bool env_step(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, in
             // every job waiting for machine m_a: no longer legal (:455-461), no longer
             // no-op-blocked (:464-467; illegal_actions[m][j] implies needed_machine[j]==m)
             if (jss_op_m(s.op[i]) == m_a) s.lb &= ~(17u << i);
-        while (!__any_sync(JSS_FULL, (s.lb & LM) != 0u) && __any_sync(JSS_FULL, s.tuam > 0))   // :469-470
-            holes += env_advance<KJ>(iv, s, lane);
-        raw_reward = d_a - holes;
     }
+    // ONE inlined copy of the time advance serves the three callers: the raw hook (exactly one
+    // advance), the no-op (:429-430, at least one) and the job branch (:469-470, zero or more)
+    bool force = wait;
+    while (force || (!__any_sync(JSS_FULL, (s.lb & LM) != 0u) && __any_sync(JSS_FULL, s.tuam > 0))) {
+        holes += env_advance<KJ>(iv, s, lane);
+        force = false;
+        if (action == JSS_ACTION_ADVANCE) { raw_reward = -holes; return true; }   // heuristics / _is_done do NOT run
+    }
+    if (action == iv.si->J && !__any_sync(JSS_FULL, (s.lb & LM) != 0u))
+        s.flags |= JSS_FLAG_ERROR;                       // the reference raises here (queue ran empty)
+    raw_reward = gain - holes;
     env_prioritize<KJ>(iv, s, lane);                     // :432 / :471
     const uint32_t ML = env_machine_legal<KJ>(s);
     const int nlegal = (int)__reduce_add_sync(JSS_FULL, (unsigned)__popc(s.lb & LM));
@@ -604,7 +607,7 @@ JSS_DEV bool env_step(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, in
 }
 
 // ---- policies (JSSEnv/dispatching.py; README.md:58-60) ---------------------------------
-template <int KJ>
+template <int KJ, bool RANDOM_ONLY = false>
 JSS_DEV int env_select_action(const InstView &iv, const EnvRegs<KJ> &s, int lane, int rule, int coin_mode,
                               uint32_t h) {
     constexpr uint32_t LM = jss_legal_mask<KJ>();
@@ -620,7 +623,7 @@ JSS_DEV int env_select_action(const InstView &iv, const EnvRegs<KJ> &s, int lane
     const bool noop = (s.flags & JSS_FLAG_NOOP_LEGAL) != 0u;
     if (s.flags & JSS_FLAG_DONE) return 0;               // ignored by step (auto-reset or frozen)
     if (njobs == 0) return noop ? iv.si->J : JSS_ACTION_SKIP;   // "only the no-op is legal" (e.g. :96-97)
-    if (rule == JSS_RULE_RANDOM) {
+    if (RANDOM_ONLY || rule == JSS_RULE_RANDOM) {
         // uniform over the set bits of action_mask, indexed in ascending action order
         const uint32_t r = jss_pick(h, (uint32_t)(njobs + (noop ? 1 : 0)));
         if ((int)r == njobs) return iv.si->J;
@@ -906,7 +909,7 @@ jss_env_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
 // while the current env is simulated, and the observation staging buffer that leaves by bulk store.
 // SAMPLE = true additionally picks every env's NEXT action (masked-uniform sampler or a
 // dispatching rule) from the freshly computed state, so a policy-driven loop is one launch per step.
-template <int KJ, bool SAMPLE>
+template <int KJ, int SAMPLE>   // 0: step only, 1: + masked-uniform sampler, 2: + any dispatching rule
 __global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, JSS_MIN_CTAS)
 jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JSS_SMEM_DECL(jss_smem);
@@ -939,7 +942,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
         jss_tile_desc(p, tile, first, inst, count);
         if (inst != staged) {                            // CTA-uniform
             __syncthreads();
-            jss_stage_instance(p, p.inst[inst], si, sm_ops, sm_len, sm_rem, SAMPLE && sl.rem_elems > 0);
+            jss_stage_instance(p, p.inst[inst], si, sm_ops, sm_len, sm_rem, SAMPLE == 2 && sl.rem_elems > 0);
             staged = inst;
             __syncthreads();
         }
@@ -965,7 +968,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
         const bool changed = env_step<KJ>(p, iv, s, env, lane, action, raw, reinterpret_cast<int *>(scratch));
         if (SAMPLE) {
             const uint32_t h = jss_hash3(a.seed, p.env_id_base + (uint64_t)env, a.step_index);
-            const int nxt = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h);
+            const int nxt = env_select_action<KJ, SAMPLE == 1>(iv, s, lane, a.rule, a.coin_mode, h);
             if (lane == 0) a.actions_out[env] = nxt;
         }
         if (changed) {
