@@ -112,6 +112,11 @@ int launch_step_variant(jss_t *h, const JssLaunch &a, bool want_rem, cudaStream_
     const int n_tiles = a.tile_end - a.tile_begin;
     JssSmemLayout sl = want_rem ? h->sl_rem : h->sl_norem;
     sl.statein_words = h->p.block_words;
+    sl.off_len = (int32_t)sizeof(SmInst) + sl.ops_elems * 2;
+    sl.off_rem = sl.off_len + sl.len_elems * 4;
+    sl.off_warp0 = sl.off_rem + sl.rem_elems * 2;
+    sl.off_scratch = 16 + sl.statein_words * 4;
+    sl.warp_stride = sl.off_scratch + sl.scratch_words * 4;
     const size_t smem = smem_bytes_step(sl);
     auto kern = jss_step_kernel<KJ, SAMPLE>;
     int &grid = h->step_grid[(KJ == 1 ? 0 : (KJ == 2 ? 1 : 2)) * 4 + SAMPLE + (want_rem ? 1 : 0)];

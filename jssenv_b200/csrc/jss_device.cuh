@@ -101,40 +101,43 @@ JSS_DEV float jss_div(float x, float y, float ry) {
 // buffer by one bulk copy (global -> shared, completion on an mbarrier) while the current env
 // is simulated; an env's observation rows leave shared memory with one bulk copy
 // (shared -> global).  Sizes/addresses are multiples of 16 bytes by construction.
+// Shared-memory operands are passed as 32-bit shared-space addresses (jss_saddr_t) computed from
+// ONE base register, so no generic<->shared address conversions are needed at the call sites.
 #ifndef JSS_EMU
-JSS_DEV uint32_t jss_smem_addr(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
-JSS_DEV void jss_mbar_init(uint64_t *mbar) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(jss_smem_addr(mbar)) : "memory");
+typedef uint32_t jss_saddr_t;
+JSS_DEV jss_saddr_t jss_saddr(const void *generic_ptr) { return (uint32_t)__cvta_generic_to_shared(generic_ptr); }
+JSS_DEV void jss_mbar_init(jss_saddr_t mbar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-JSS_DEV void jss_bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *mbar) {
-    const uint32_t mb = jss_smem_addr(mbar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+JSS_DEV void jss_bulk_load(jss_saddr_t smem_dst, const void *gmem_src, uint32_t bytes, jss_saddr_t mbar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(jss_smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(mb) : "memory");
+                 ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(mbar) : "memory");
 }
-JSS_DEV void jss_mbar_wait(uint64_t *mbar, uint32_t phase) {
-    const uint32_t mb = jss_smem_addr(mbar);
+JSS_DEV void jss_mbar_wait(jss_saddr_t mbar, uint32_t phase) {
     uint32_t ok;
     do {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(mb), "r"(phase) : "memory");
+                     : "=r"(ok) : "r"(mbar), "r"(phase) : "memory");
     } while (!ok);
 }
 JSS_DEV void jss_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-JSS_DEV void jss_bulk_store(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+JSS_DEV void jss_bulk_store(void *gmem_dst, jss_saddr_t smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 ::"l"(gmem_dst), "r"(jss_smem_addr(smem_src)), "r"(bytes) : "memory");
+                 ::"l"(gmem_dst), "r"(smem_src), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 JSS_DEV void jss_bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 JSS_DEV void jss_bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 #else   // host emulation (tests/emu): synchronous copies; the waits are warp rendezvous points
-JSS_DEV void jss_mbar_init(uint64_t *mbar) { *mbar = 0; }
-JSS_DEV void jss_bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *) { memcpy(smem_dst, gmem_src, bytes); }
-JSS_DEV void jss_mbar_wait(uint64_t *, uint32_t) { __syncwarp(); }
+typedef char *jss_saddr_t;
+JSS_DEV jss_saddr_t jss_saddr(const void *generic_ptr) { return (char *)generic_ptr; }
+JSS_DEV void jss_mbar_init(jss_saddr_t) {}
+JSS_DEV void jss_bulk_load(jss_saddr_t smem_dst, const void *gmem_src, uint32_t bytes, jss_saddr_t) { memcpy(smem_dst, gmem_src, bytes); }
+JSS_DEV void jss_mbar_wait(jss_saddr_t, uint32_t) { __syncwarp(); }
 JSS_DEV void jss_fence_async_smem() {}
-JSS_DEV void jss_bulk_store(void *gmem_dst, const void *smem_src, uint32_t bytes) { memcpy(gmem_dst, smem_src, bytes); }
+JSS_DEV void jss_bulk_store(void *gmem_dst, jss_saddr_t smem_src, uint32_t bytes) { memcpy(gmem_dst, smem_src, bytes); }
 JSS_DEV void jss_bulk_store_wait_read() {}
 JSS_DEV void jss_bulk_store_wait_all() {}
 #endif
@@ -406,6 +409,7 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
     // pass 2 (:324-401): jobs that are not legal now but may need a legal machine soon
     uint32_t want = 0u;
     const int row = KJ * lane * iv.si->M;
+    const int last = iv.si->M - 1;
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
         // countdown of the job's current machine (case 2, :374-377)
@@ -414,9 +418,9 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
             int ts, tm;
             if (s.tufco[i] > 0) { ts = s.todo[i] + 1; tm = s.t + s.tufco[i]; }      // case 1 (:327-337); a running
             else if (!(s.lb & (16u << i))) { ts = s.todo[i]; tm = s.t + tq; }       // last op walks nothing either way
-            else { ts = iv.si->M; tm = 0; }                                             // case 2 (:366-377) / blocked
+            else { ts = iv.si->M; tm = 0; }                                         // case 2 (:366-377) / blocked
             const uint16_t *o_ptr = iv.ops + row + i * iv.si->M;
-            while (ts < iv.si->M - 1 && maxh > tm) {                                    // :340-342 / :380-382
+            while (ts < last && maxh > tm) {                                        // :340-342 / :380-382
                 const uint32_t o = o_ptr[ts];
                 if (hz[jss_op_m(o)] > tm) want |= 1u << jss_op_m(o);                // machine_next.add (:351 / :391)
                 tm += jss_op_d(o);
@@ -432,7 +436,7 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
 // ---- observation / mask / reward (jss_env.py:102-134, 483-493) ---------------------
 template <int KJ, bool BULK = false>
 JSS_DEV void env_emit_obs(const JssParams &p, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane,
-                          float *scratch) {
+                          float *scratch, jss_saddr_t scratch_sa = jss_saddr_t()) {
     if (KJ * lane < iv.si->J) {
         float v[KJ * 7];
 #pragma unroll
@@ -469,7 +473,7 @@ JSS_DEV void env_emit_obs(const JssParams &p, const InstView &iv, const EnvRegs<
         // ... and hand the env's J*7 floats to the TMA engine: one bulk copy shared -> global
         jss_fence_async_smem();          // make the generic-proxy writes visible to the async proxy
         __syncwarp();
-        if (lane == 0) jss_bulk_store(dst, scratch, (uint32_t)n * 4u);
+        if (lane == 0) jss_bulk_store(dst, scratch_sa, (uint32_t)n * 4u);
         return;                          // the caller waits (wait_group.read) before reusing `scratch`
     }
     __syncwarp();
@@ -733,6 +737,9 @@ JSS_DEV void env_import(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, 
 struct JssSmemLayout {      // element counts; every region starts 16-byte aligned
     int32_t ops_elems, len_elems, rem_elems, scratch_words;
     int32_t statein_words;  // step kernel only: per-warp state-block prefetch buffer
+    // byte offsets from the start of dynamic shared memory, precomputed on the host so the
+    // kernel derives every pointer with one add: [SmInst][ops][len][rem][per-warp regions]
+    int32_t off_len, off_rem, off_warp0, warp_stride, off_scratch;   // off_scratch: inside a warp region
 };
 
 JSS_DEV void jss_stage_instance(const JssParams &p, const JssInstDesc &d, SmInst *si, uint16_t *sm_ops,
@@ -768,8 +775,8 @@ JSS_DEV void jss_stage_instance(const JssParams &p, const JssInstDesc &d, SmInst
 
 template <int KJ, bool BULK = false>
 JSS_DEV void env_emit_all(const JssParams &p, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane,
-                          float *scratch, int raw) {
-    env_emit_obs<KJ, BULK>(p, iv, s, env, lane, scratch);
+                          float *scratch, int raw, jss_saddr_t scratch_sa = jss_saddr_t()) {
+    env_emit_obs<KJ, BULK>(p, iv, s, env, lane, scratch, scratch_sa);
     env_emit_mask<KJ>(p, iv, s, env, lane, (s.flags & JSS_FLAG_NOOP_LEGAL) != 0u);
     env_emit_scalars<KJ>(p, iv, s, env, lane, raw);
 }
@@ -913,16 +920,17 @@ template <int KJ, int SAMPLE>   // 0: step only, 1: + masked-uniform sampler, 2:
 __global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, JSS_MIN_CTAS)
 jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JSS_SMEM_DECL(jss_smem);
-    SmInst *si = reinterpret_cast<SmInst *>(jss_smem);
-    uint16_t *sm_ops = reinterpret_cast<uint16_t *>(si + 1);
-    int32_t *sm_len = reinterpret_cast<int32_t *>(sm_ops + sl.ops_elems);
+    char *sm = reinterpret_cast<char *>(jss_smem);
+    SmInst *si = reinterpret_cast<SmInst *>(sm);
+    uint16_t *sm_ops = reinterpret_cast<uint16_t *>(sm + sizeof(SmInst));
+    int32_t *sm_len = reinterpret_cast<int32_t *>(sm + sl.off_len);
+    uint16_t *sm_rem = reinterpret_cast<uint16_t *>(sm + sl.off_rem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint16_t *sm_rem = reinterpret_cast<uint16_t *>(sm_len + sl.len_elems);
-    int32_t *wbase = reinterpret_cast<int32_t *>(sm_rem + sl.rem_elems) +
-                     (size_t)warp * (4 + sl.statein_words + sl.scratch_words);
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(wbase);
-    int32_t *state_in = wbase + 4;
-    float *scratch = reinterpret_cast<float *>(state_in + sl.statein_words);
+    char *wbase = sm + sl.off_warp0 + warp * sl.warp_stride;
+    int32_t *state_in = reinterpret_cast<int32_t *>(wbase + 16);
+    float *scratch = reinterpret_cast<float *>(wbase + sl.off_scratch);
+    const jss_saddr_t mbar = jss_saddr(sm) + (sl.off_warp0 + warp * sl.warp_stride);   // shared-space addresses
+    const jss_saddr_t state_sa = mbar + 16, scratch_sa = mbar + sl.off_scratch;
     const uint32_t blk_bytes = (uint32_t)p.block_words * 4u;
     if (lane == 0) jss_mbar_init(mbar);
     __syncwarp();
@@ -934,7 +942,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     int env_next = jss_tile_env(p, tile, a.tile_end, warp);
     int act_next = 0;
     if (env_next >= 0) {
-        if (lane == 0) jss_bulk_load(state_in, p.state + (size_t)env_next * p.block_words, blk_bytes, mbar);
+        if (lane == 0) jss_bulk_load(state_sa, p.state + (size_t)env_next * p.block_words, blk_bytes, mbar);
         act_next = a.actions[env_next];
     }
     for (; tile < a.tile_end; tile += (int)gridDim.x) {
@@ -956,7 +964,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
             __syncwarp();                                // every lane has read the buffer
         }
         if (env_next >= 0) {                             // prefetch the next env's block + action
-            if (lane == 0) jss_bulk_load(state_in, p.state + (size_t)env_next * p.block_words, blk_bytes, mbar);
+            if (lane == 0) jss_bulk_load(state_sa, p.state + (size_t)env_next * p.block_words, blk_bytes, mbar);
             act_next = a.actions[env_next];
         }
         if (env < 0) continue;
@@ -973,7 +981,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
         }
         if (changed) {
             env_store<KJ>(p, iv, env, lane, s);
-            env_emit_all<KJ, true>(p, iv, s, env, lane, scratch, raw);
+            env_emit_all<KJ, true>(p, iv, s, env, lane, scratch, raw, scratch_sa);
         } else if (s.flags != flags_in) {                // only the sticky error bit changed
             if (lane == 0) {
                 p.state[(size_t)env * p.block_words + 5 * p.Jcap + p.Mcap + 8 + JSS_HDR_FLAGS] = (int32_t)s.flags;
