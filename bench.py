@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
     ap.add_argument("--instance", default="ta80")
-    ap.add_argument("--e2e-steps", type=int, default=60)
+    ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--steps-ref", type=int, default=1)
     ap.add_argument("--warmup-ref", type=int, default=0)
@@ -245,23 +245,38 @@ def main():
     # ---- e2e: the same transitions through the host-buffer API (H2D actions, D2H obs/mask/reward/done)
     e2e = None
     if not args.no_e2e:
+        # pipelined host-buffer API: begin(step k) -> wait mask k -> host policy -> begin(step k+1) while the
+        # 2.9 KB/env observation of step k is still crossing PCIe into its own pinned buffer -> consume obs k
         env.reset()
-        obs, _, _, _, _ = env.step_host(env.host_masked_random(np.ascontiguousarray(env.action_mask.cpu().numpy()), 0))
-        for k in range(3):
-            obs, _, _, _, _ = env.step_host(env.host_masked_random(obs["action_mask"], 1 + k))
+        mask = np.ascontiguousarray(env.action_mask.cpu().numpy())
+        env.host_step_begin(env.host_masked_random(mask, 0))
+        checksum = 0.0
+
+        def e2e_step(k):
+            m, rew, dn = env.host_wait_mask()
+            env.host_step_begin(env.host_masked_random(m, k))
+            return env.host_wait_obs(previous=True)      # the step's observation, on the host
+
+        for k in range(1, 4):
+            e2e_step(k)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for k in range(args.e2e_steps):
-            obs, rew, dn, _, _ = env.step_host(env.host_masked_random(obs["action_mask"], 10 + k))
+            obs_host = e2e_step(10 + k)
+            checksum += float(obs_host[0, 0, 0])          # touch the result
+        env.host_wait_obs()
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * N * args.e2e_steps / float(dt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": N * (J + 1) + N * J * 7 * 4 + 4 * N + N,
-               "steps": args.e2e_steps, "note": "host masked-random policy + jss_step_host (pinned host buffers)"}
+               "h2d_bytes_per_step": 4 * N,
+               "d2h_bytes_per_step": N * int(env._b.mask_stride) + N * J * 7 * 4 + 16 * N,
+               "steps": args.e2e_steps,
+               "note": "jss_host_step_begin / jss_host_wait (pinned host buffers): H2D actions, step kernel, D2H mask + "
+                       "scalars + real_obs every step; host masked-random policy from the host mask; PCIe-bound"}
 
     if rank == 0:
         peak, peak_src = load_peaks()

@@ -194,6 +194,20 @@ int jss_rollout(jss_t *h, int rule, uint64_t seed, uint64_t step_index, int n_st
 int jss_step_host(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, float *obs_host,
                   int32_t *scalars_host, void *stream);
 
+/* Pipelined host-buffer stepping (the e2e path).  jss_host_step_begin enqueues, on internal
+ * streams, H2D of the actions, the step kernel, D2H of mask + scalar records (small, first) and
+ * the D2H of real_obs via a device staging copy, and returns immediately.
+ * jss_host_wait(JSS_WAIT_MASK) blocks until mask/scalars of the latest begin have landed (enough
+ * for a host policy to choose the next actions); JSS_WAIT_OBS until its observation has landed.
+ * A new begin may follow WAIT_MASK while the previous observation is still streaming into ITS host
+ * buffer (callers alternate two pinned observation buffers and call WAIT_OBS before reading one). */
+#define JSS_WAIT_MASK 1
+#define JSS_WAIT_OBS 2       /* observation of the latest begin */
+#define JSS_WAIT_OBS_PREV 3  /* observation of the begin before the latest one */
+int jss_host_step_begin(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, float *obs_host,
+                        int32_t *scalars_host);
+int jss_host_wait(jss_t *h, int what);
+
 /* --- auxiliary ----------------------------------------------------------- */
 
 /* Per-shard statistics (host int64[JSS_STATS_LEN]); synchronises `stream`. */

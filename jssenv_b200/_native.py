@@ -18,6 +18,7 @@ ACTION_SKIP, ACTION_ADVANCE = -1, -2
 CREATE_AUTO_RESET, CREATE_RECORD_SOLUTION = 1, 2
 FLAG_DONE, FLAG_ERROR, FLAG_NOOP_LEGAL = 1, 2, 4
 COIN_DEVICE, COIN_NEVER = 0, 1
+WAIT_MASK, WAIT_OBS, WAIT_OBS_PREV = 1, 2, 3
 RULES = {"RANDOM": 0, "SPT": 1, "FIFO": 2, "MWR": 3, "LWR": 4, "MOR": 5, "LOR": 6, "CR": 7}
 STATS_KEYS = ("episodes", "steps", "sum_makespan", "min_makespan", "max_makespan", "sum_return",
               "envs_done", "envs_error")
@@ -25,7 +26,7 @@ STATS_KEYS = ("episodes", "steps", "sum_makespan", "min_makespan", "max_makespan
 EXPORTED_SYMBOLS = (
     "jss_abi_version", "jss_create", "jss_destroy", "jss_last_error", "jss_load_instances", "jss_assign",
     "jss_get_buffers", "jss_instance_scalars", "jss_reset", "jss_step", "jss_policy", "jss_rollout",
-    "jss_step_host", "jss_step_sample", "jss_stats", "jss_export_state", "jss_import_state", "jss_host_masked_random",
+    "jss_step_host", "jss_host_step_begin", "jss_host_wait", "jss_step_sample", "jss_stats", "jss_export_state", "jss_import_state", "jss_host_masked_random",
     "jss_launch_count",
 )
 
@@ -64,6 +65,8 @@ def _declare(L):
     L.jss_step_sample.argtypes = [c_void_p, c_void_p, c_int, c_int, c_uint64, c_uint64, c_void_p, c_void_p]
     L.jss_rollout.argtypes = [c_void_p, c_int, c_uint64, c_uint64, c_int, c_int, c_void_p]
     L.jss_step_host.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.jss_host_step_begin.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.jss_host_wait.argtypes = [c_void_p, c_int]
     L.jss_stats.argtypes = [c_void_p, POINTER(c_int64), c_void_p]
     L.jss_export_state.argtypes = [c_void_p, c_void_p]
     L.jss_import_state.argtypes = [c_void_p, c_void_p, c_void_p]
@@ -71,7 +74,7 @@ def _declare(L):
     L.jss_launch_count.argtypes = [c_void_p]
     L.jss_launch_count.restype = c_int64
     for name in ("jss_create", "jss_load_instances", "jss_assign", "jss_get_buffers", "jss_instance_scalars",
-                 "jss_reset", "jss_step", "jss_policy", "jss_rollout", "jss_step_host", "jss_step_sample", "jss_stats",
+                 "jss_reset", "jss_step", "jss_policy", "jss_rollout", "jss_step_host", "jss_host_step_begin", "jss_host_wait", "jss_step_sample", "jss_stats",
                  "jss_export_state", "jss_import_state", "jss_host_masked_random"):
         getattr(L, name).restype = c_int
     return L

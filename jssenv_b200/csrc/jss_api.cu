@@ -58,9 +58,14 @@ struct jss_handle {
     int step_grid[12] = {0};
     std::vector<int32_t> env_inst;
 
-    // pinned staging for jss_step_host
+    // host-buffer stepping
     int32_t *pin_actions = nullptr;
     int32_t *dev_actions = nullptr;
+    float *obs_staging = nullptr;                  // pipelined mode: device copy the D2H engine reads from
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_mask = nullptr, ev_staged = nullptr, ev_obs[2] = {nullptr, nullptr};
+    int pipe_cur = 0;                              // which ev_obs belongs to the latest begin
+    bool pipe_ready = false;
 };
 
 namespace {
@@ -235,6 +240,11 @@ int jss_create(jss_t **out, int device, int n_envs, uint32_t flags, uint64_t env
 void jss_destroy(jss_t *h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    if (h->pipe_ready) {
+        cudaStreamSynchronize(h->s_compute); cudaStreamSynchronize(h->s_copy);
+        cudaEventDestroy(h->ev_mask); cudaEventDestroy(h->ev_staged); cudaEventDestroy(h->ev_obs[0]); cudaEventDestroy(h->ev_obs[1]);
+        cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy);
+    }
     for (void *ptr : h->allocs) cudaFree(ptr);
     if (h->pin_actions) cudaFreeHost(h->pin_actions);
     delete h;
@@ -541,6 +551,59 @@ int jss_step_host(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, flo
     return JSS_OK;
 }
 
+int jss_host_step_begin(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, float *obs_host,
+                        int32_t *scalars_host) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!actions_host) return fail(h, JSS_ERR_INVALID, "jss_host_step_begin: actions_host is NULL");
+    const JssParams &p = h->p;
+    const size_t N = (size_t)p.n_envs, obs_bytes = N * p.jobs_max * 7 * 4;
+    if (!h->pipe_ready) {
+        if ((rc = dev_alloc(h, &h->obs_staging, N * p.jobs_max * 7, false))) return rc;
+        JSS_CUDA(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+        JSS_CUDA(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+        JSS_CUDA(h, cudaEventCreateWithFlags(&h->ev_mask, cudaEventDisableTiming));
+        JSS_CUDA(h, cudaEventCreateWithFlags(&h->ev_staged, cudaEventDisableTiming));
+        for (int k = 0; k < 2; k++) {
+            JSS_CUDA(h, cudaEventCreateWithFlags(&h->ev_obs[k], cudaEventDisableTiming));
+            JSS_CUDA(h, cudaEventRecord(h->ev_obs[k], h->s_copy));
+        }
+        h->pipe_ready = true;
+    }
+    cudaStream_t sc = h->s_compute;
+    JSS_CUDA(h, cudaMemcpyAsync(h->dev_actions, actions_host, N * 4, cudaMemcpyHostToDevice, sc));
+    rc = jss_step(h, h->dev_actions, (void *)sc);
+    if (rc) return rc;
+    // the small results first: a host policy only needs the mask
+    if (mask_host) JSS_CUDA(h, cudaMemcpyAsync(mask_host, p.mask, N * p.mask_stride, cudaMemcpyDeviceToHost, sc));
+    if (scalars_host) JSS_CUDA(h, cudaMemcpyAsync(scalars_host, p.scalars, N * 16, cudaMemcpyDeviceToHost, sc));
+    JSS_CUDA(h, cudaEventRecord(h->ev_mask, sc));
+    const int prev = h->pipe_cur;
+    h->pipe_cur ^= 1;
+    if (obs_host) {
+        // observation: device-side staging copy (so the next step may overwrite real_obs), then the
+        // 2.9 KB/env PCIe transfer on its own stream, overlapping the host policy and the next launch
+        JSS_CUDA(h, cudaStreamWaitEvent(sc, h->ev_obs[prev], 0));      // previous D2H has drained the staging copy
+        JSS_CUDA(h, cudaMemcpyAsync(h->obs_staging, p.obs, obs_bytes, cudaMemcpyDeviceToDevice, sc));
+        JSS_CUDA(h, cudaEventRecord(h->ev_staged, sc));
+        JSS_CUDA(h, cudaStreamWaitEvent(h->s_copy, h->ev_staged, 0));
+        JSS_CUDA(h, cudaMemcpyAsync(obs_host, h->obs_staging, obs_bytes, cudaMemcpyDeviceToHost, h->s_copy));
+    }
+    JSS_CUDA(h, cudaEventRecord(h->ev_obs[h->pipe_cur], h->s_copy));
+    return JSS_OK;
+}
+
+int jss_host_wait(jss_t *h, int what) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!h->pipe_ready) return fail(h, JSS_ERR_STATE, "jss_host_wait: no jss_host_step_begin in flight");
+    if (what == JSS_WAIT_MASK) JSS_CUDA(h, cudaEventSynchronize(h->ev_mask));
+    else if (what == JSS_WAIT_OBS) JSS_CUDA(h, cudaEventSynchronize(h->ev_obs[h->pipe_cur]));
+    else if (what == JSS_WAIT_OBS_PREV) JSS_CUDA(h, cudaEventSynchronize(h->ev_obs[h->pipe_cur ^ 1]));
+    else return fail(h, JSS_ERR_INVALID, "jss_host_wait: unknown selector %d", what);
+    return JSS_OK;
+}
+
 int jss_stats(jss_t *h, int64_t *out_host, void *stream) {
     int rc = check_ready(h);
     if (rc) return rc;
@@ -595,8 +658,13 @@ int jss_host_masked_random(const uint8_t *mask_host, int n, int width, int64_t r
             actions_host[e] = act;
         }
     };
-    const int nthreads = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()),
-                                               std::max<size_t>(1, (size_t)n * width / (1 << 18)));
+    size_t cpus = std::max(1u, std::thread::hardware_concurrency());
+    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {          // container CPU quota, if any
+        long long q = 0, per = 0;
+        if (fscanf(f, "%lld %lld", &q, &per) == 2 && q > 0 && per > 0) cpus = std::min<size_t>(cpus, (size_t)((q + per - 1) / per));
+        fclose(f);
+    }
+    const int nthreads = (int)std::min<size_t>(cpus, std::max<size_t>(1, (size_t)n * width / (1 << 18)));
     if (nthreads <= 1) { work(0, n); return JSS_OK; }
     std::vector<std::thread> pool;
     const int chunk = (n + nthreads - 1) / nthreads;

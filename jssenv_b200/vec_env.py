@@ -207,6 +207,43 @@ class JssVecEnv:
         obs = {"real_obs": hv["obs"], "action_mask": hv["mask"]}
         return obs, hv["reward"], hv["done"], np.zeros(n, np.bool_), {}
 
+    # pipelined form: begin -> wait_mask -> (choose next actions) -> begin ... ; obs lands in alternating buffers
+    def host_step_begin(self, actions: np.ndarray):
+        """Enqueue one host-buffer step and return immediately (see jss_host_step_begin).  Results land
+        in this call's slot of two alternating pinned buffer sets; use host_wait_mask()/host_wait_obs()."""
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        n, J = self.num_envs, self.jobs
+        if not hasattr(self, "_pipe"):
+            import torch
+            pin = N.backend.name == "cuda"
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin)   # noqa: E731
+            ms = int(self._b.mask_stride)
+            self._pipe = [{"mask": mk((n, ms), torch.uint8), "obs": mk((n, J, 7), torch.float32),
+                           "scalars": mk((n, 4), torch.int32), "actions": mk((n,), torch.int32)} for _ in range(2)]
+            self._pipe_slot = 0
+        self._pipe_slot ^= 1
+        b = self._pipe[self._pipe_slot]
+        b["actions"].numpy()[:] = a                      # pinned copy: the H2D must not race with the caller's array
+        rc = self._L.jss_host_step_begin(self._h, ctypes.c_void_p(b["actions"].data_ptr()),
+                                         ctypes.c_void_p(b["mask"].data_ptr()), ctypes.c_void_p(b["obs"].data_ptr()),
+                                         ctypes.c_void_p(b["scalars"].data_ptr()))
+        N.check(self._h, rc, "jss_host_step_begin")
+        return self._pipe_slot
+
+    def host_wait_mask(self):
+        """Block until mask / reward / done of the latest host_step_begin have landed; returns them."""
+        N.check(self._h, self._L.jss_host_wait(self._h, N.WAIT_MASK), "jss_host_wait")
+        b = self._pipe[self._pipe_slot]
+        sc = b["scalars"].numpy()
+        return (b["mask"].numpy()[:, : self.jobs + 1].view(np.bool_), sc.view(np.float32)[:, 0],
+                sc.view(np.uint8)[:, 12].view(np.bool_))
+
+    def host_wait_obs(self, previous: bool = False):
+        """Block until the observation of the latest host_step_begin (or, with previous=True, of the one
+        before it, which may be consumed while the latest is still streaming) has landed; returns (N, J, 7)."""
+        N.check(self._h, self._L.jss_host_wait(self._h, N.WAIT_OBS_PREV if previous else N.WAIT_OBS), "jss_host_wait")
+        return self._pipe[self._pipe_slot ^ (1 if previous else 0)]["obs"].numpy()
+
     def host_masked_random(self, mask: np.ndarray, step_index: int) -> np.ndarray:
         """Same draw as policy('RANDOM') but from a host mask (for host-side agents / tests)."""
         m = np.asarray(mask)

@@ -416,3 +416,24 @@ def check_step_sample(make_env, names, rule, n_steps, seed):
             assert np.array_equal(_np(getattr(a_env, name)), _np(getattr(b_env, name))), (k, name)
     assert a_env.stats() == b_env.stats()
     return a_env
+
+
+def check_host_pipeline(make_env, name, seed):
+    """The pipelined host-buffer path (begin / wait_mask / wait_obs) == the device-resident path."""
+    env = make_env(7, {"instance_path": name}, seed=seed)
+    ref = make_env(7, {"instance_path": name}, seed=seed)
+    env.reset(); ref.reset()
+    mask = np.ascontiguousarray(_np(env.action_mask))
+    a = env.host_masked_random(mask, 0)
+    env.host_step_begin(a)
+    for k in range(1, 80):
+        mask, rew, done = env.host_wait_mask()
+        ref.step(a)
+        assert np.array_equal(mask, _np(ref.action_mask)), k
+        assert np.array_equal(rew, _np(ref.reward)) and np.array_equal(done, _np(ref.done))
+        nxt = env.host_masked_random(mask, k)
+        obs_prev_expected = _np(ref.real_obs).copy()
+        env.host_step_begin(nxt)                       # next step enqueued while the previous obs may still stream
+        assert np.array_equal(env.host_wait_obs(previous=True), obs_prev_expected), k
+        a = nxt
+    return env

@@ -85,3 +85,7 @@ def test_emu_step_host():
 @pytest.mark.parametrize("rule", ["RANDOM", "MWR"])
 def test_emu_step_sample_fused(rule):
     pc.check_step_sample(make_env, ["ta01", "ta51", "ta80"], rule, n_steps=300, seed=12)
+
+
+def test_emu_host_pipeline():
+    pc.check_host_pipeline(make_env, "ta01", seed=3)

@@ -213,3 +213,8 @@ def test_gpu_config5_mixed_ta01_ta80_rules():
                 _, _, done, _, _ = o.step(a)
                 step += 1
             assert int(mk[i]) == o.current_time_step, (rule, i)
+
+
+def test_gpu_host_pipeline():
+    pc.check_host_pipeline(make_env, "ta01", seed=3)
+    pc.check_host_pipeline(make_env, "ta80", seed=4)
