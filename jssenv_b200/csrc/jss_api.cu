@@ -574,9 +574,24 @@ int jss_host_step_begin(jss_t *h, const int32_t *actions_host, uint8_t *mask_hos
     JSS_CUDA(h, cudaMemcpyAsync(h->dev_actions, actions_host, N * 4, cudaMemcpyHostToDevice, sc));
     rc = jss_step(h, h->dev_actions, (void *)sc);
     if (rc) return rc;
-    // the small results first: a host policy only needs the mask
-    if (mask_host) JSS_CUDA(h, cudaMemcpyAsync(mask_host, p.mask, N * p.mask_stride, cudaMemcpyDeviceToHost, sc));
-    if (scalars_host) JSS_CUDA(h, cudaMemcpyAsync(scalars_host, p.scalars, N * 16, cudaMemcpyDeviceToHost, sc));
+    // the small results first: a host policy only needs the mask.  If the host buffers are pinned
+    // (device-mappable) the SMs write them directly; otherwise fall back to the copy engine.
+    auto small_d2h = [&](void *dst_host, const void *src_dev, size_t bytes) -> int {
+        void *mapped = nullptr;
+        if ((bytes & 15) == 0 && cudaHostGetDevicePointer(&mapped, dst_host, 0) == cudaSuccess && mapped) {
+            const size_t n16 = bytes / 16;
+            const int blocks = (int)std::min<size_t>((n16 + 255) / 256, (size_t)h->sm_count * 8);
+            JSS_LAUNCH(jss_copy16_kernel, blocks, 256, 0, sc, (uint4 *)mapped, (const uint4 *)src_dev, n16);
+            JSS_CUDA(h, cudaGetLastError());
+            h->launches += 1;
+        } else {
+            (void)cudaGetLastError();
+            JSS_CUDA(h, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, sc));
+        }
+        return JSS_OK;
+    };
+    if (mask_host && (rc = small_d2h(mask_host, p.mask, N * p.mask_stride))) return rc;
+    if (scalars_host && (rc = small_d2h(scalars_host, p.scalars, N * 16))) return rc;
     JSS_CUDA(h, cudaEventRecord(h->ev_mask, sc));
     const int prev = h->pipe_cur;
     h->pipe_cur ^= 1;

@@ -993,6 +993,14 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     if (lane == 0) jss_bulk_store_wait_all();            // shared memory must outlive the bulk reads
 }
 
+// ---- SM-driven copy of small results into mapped pinned host memory -------------------------
+// (mask + scalar records, ~8 MB per step at N = 65 536).  Posted PCIe writes from the SMs do not
+// queue behind the 183 MB observation transfer that occupies the D2H copy engine.
+__global__ void jss_copy16_kernel(uint4 *dst, const uint4 *src, size_t n16) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
 // ---- per-shard statistics ------------------------------------------------------------------
 __global__ void jss_stats_kernel(const JssParams p, unsigned long long *out) {
     // out[0..7] pre-initialised by the host: sums 0, min = ~0ull

@@ -100,6 +100,8 @@ template <typename A, typename B, typename C>
 void launch(void (*k)(A, B, C), dim3 g, dim3 b, size_t smem, A a, B bb, C c) { Pack<A, B, C> p{k, a, bb, c}; launch_impl(&Pack<A, B, C>::run, &p, g, b, smem); }
 template <typename A, typename B>
 void launch(void (*k)(A, B), dim3 g, dim3 b, size_t smem, A a, B bb) { Pack<A, B> p{k, a, bb}; launch_impl(&Pack<A, B>::run, &p, g, b, smem); }
+template <typename A, typename B, typename C, typename A2, typename B2, typename C2>
+void launch(void (*k)(A, B, C), dim3 g, dim3 b, size_t smem, A2 a, B2 bb, C2 c) { Pack<A, B, C> p{k, (A)a, (B)bb, (C)c}; launch_impl(&Pack<A, B, C>::run, &p, g, b, smem); }
 }  // namespace emu
 #define JSS_LAUNCH(kern, grid, block, smem, stream, ...) emu::launch(kern, dim3(grid), dim3(block), smem, __VA_ARGS__)
 
@@ -124,6 +126,7 @@ static inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, s
     return 0;
 }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned) { *d = h; return 0; }
 typedef void *cudaEvent_t;
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return 0; }
