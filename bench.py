@@ -282,6 +282,13 @@ def main():
         peak, peak_src = load_peaks()
         balg = b_alg(J, M)
         achieved = balg * N / (step_kernel_ms * 1e-3) / 1e9
+        traffic = None                                   # dram__bytes_read+write per launch from the committed ncu capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj["n_envs"] == N and tj["instance"] == args.instance:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -292,7 +299,7 @@ def main():
                        "bytes_per_env_step": balg},
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "jss_step_kernel<4, sample>", "kernel_ms": step_kernel_ms,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": balg * N, "kernel": "jss_step_kernel<4, sample>", "kernel_ms": step_kernel_ms,
                          "peak_source": peak_src},
             "episode_stats": stats,
         }
