@@ -107,11 +107,6 @@ size_t smem_bytes(const JssSmemLayout &sl) {
     return sizeof(SmInst) + (size_t)sl.ops_elems * 2 + (size_t)sl.len_elems * 4 + (size_t)sl.rem_elems * 2 +
            (size_t)JSS_WARPS_PER_CTA * sl.scratch_words * 4;
 }
-size_t smem_bytes_step(const JssSmemLayout &sl) {
-    return sizeof(SmInst) + (size_t)sl.ops_elems * 2 + (size_t)sl.len_elems * 4 + (size_t)sl.rem_elems * 2 +
-           (size_t)JSS_WARPS_PER_CTA * (4 + sl.statein_words + sl.scratch_words) * 4;
-}
-
 template <int KJ, int SAMPLE>
 int launch_step_variant(jss_t *h, const JssLaunch &a, bool want_rem, cudaStream_t st) {
     const int n_tiles = a.tile_end - a.tile_begin;
@@ -121,8 +116,8 @@ int launch_step_variant(jss_t *h, const JssLaunch &a, bool want_rem, cudaStream_
     sl.off_rem = sl.off_len + sl.len_elems * 4;
     sl.off_warp0 = sl.off_rem + sl.rem_elems * 2;
     sl.off_scratch = 16 + sl.statein_words * 4;
-    sl.warp_stride = sl.off_scratch + sl.scratch_words * 4;
-    const size_t smem = smem_bytes_step(sl);
+    sl.warp_stride = sl.off_scratch + sl.scratch_words * 4 + sl.statein_words * 4;   // + state-out staging
+    const size_t smem = (size_t)sl.off_warp0 + (size_t)JSS_WARPS_PER_CTA * sl.warp_stride;
     auto kern = jss_step_kernel<KJ, SAMPLE>;
     int &grid = h->step_grid[(KJ == 1 ? 0 : (KJ == 2 ? 1 : 2)) * 4 + SAMPLE + (want_rem ? 1 : 0)];
     if (grid == 0) {                                     // once per handle: opt-in smem + occupancy

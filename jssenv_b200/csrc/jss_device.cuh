@@ -235,14 +235,9 @@ JSS_DEV void env_load_for_policy(const JssParams &p, const InstView &iv, int env
 }
 
 template <int KJ>
-JSS_DEV void env_store(const JssParams &p, const InstView &iv, int env, int lane, const EnvRegs<KJ> &s) {
-    int32_t *blk = p.state + (size_t)env * p.block_words;
+JSS_DEV void env_store_to(const JssParams &p, const InstView &iv, int32_t *blk, int lane, const EnvRegs<KJ> &s) {
     const int Jc = p.Jcap;
-    // all lanes must have finished env_load (every lane reads the shared header words)
-    // before any lane overwrites the block: paths such as the auto-reset have no
-    // collective between load and store
-    __syncwarp();
-    if (KJ * lane < iv.si->J) {
+    if (KJ * lane < Jc) {       // lanes past the last job hold the "finished job" padding values: the whole block is defined
         int32_t *q = blk + KJ * lane;
         jss_st<KJ>(q, s.todo);
         jss_st<KJ>(q + Jc, s.tufco);
@@ -251,10 +246,19 @@ JSS_DEV void env_store(const JssParams &p, const InstView &iv, int env, int lane
         jss_st<KJ>(q + 4 * Jc, s.col4);
     }
     int32_t *tail = blk + 5 * Jc;
-    if (lane < iv.si->M) tail[lane] = s.tuam;
+    if (lane < p.Mcap) tail[lane] = (lane < iv.si->M) ? s.tuam : 0;
     reinterpret_cast<uint8_t *>(tail + p.Mcap)[lane] = (uint8_t)s.lb;
     if (lane == 0)
         *reinterpret_cast<int4 *>(tail + p.Mcap + 8) = make_int4(s.t, (int)s.flags, s.ep_steps, s.ep_return);
+}
+
+template <int KJ>
+JSS_DEV void env_store(const JssParams &p, const InstView &iv, int env, int lane, const EnvRegs<KJ> &s) {
+    // all lanes must have finished env_load (every lane reads the shared header words)
+    // before any lane overwrites the block: paths such as the auto-reset have no
+    // collective between load and store
+    __syncwarp();
+    env_store_to<KJ>(p, iv, p.state + (size_t)env * p.block_words, lane, s);
 }
 
 // jss_env.py:145-181
@@ -875,7 +879,7 @@ JSS_DEV int jss_tile_env(const JssParams &p, int tile, int tile_end, int warp) {
 }
 
 #ifndef JSS_MIN_CTAS
-#define JSS_MIN_CTAS 4   // 64 registers -> 4 CTAs = 32 warps per SM (sweep in profiles/r01_notes.md)
+#define JSS_MIN_CTAS 3   // 78 registers, no spills -> 3 CTAs = 24 warps per SM (sweeps in profiles/)
 #endif
 
 template <int KJ, int MODE>
@@ -931,6 +935,9 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     float *scratch = reinterpret_cast<float *>(wbase + sl.off_scratch);
     const jss_saddr_t mbar = jss_saddr(sm) + (sl.off_warp0 + warp * sl.warp_stride);   // shared-space addresses
     const jss_saddr_t state_sa = mbar + 16, scratch_sa = mbar + sl.off_scratch;
+    // state-out staging sits right behind the observation staging (both leave by bulk store)
+    int32_t *state_out = reinterpret_cast<int32_t *>(scratch + sl.scratch_words);
+    const jss_saddr_t state_out_sa = scratch_sa + sl.scratch_words * 4;
     const uint32_t blk_bytes = (uint32_t)p.block_words * 4u;
     if (lane == 0) jss_mbar_init(mbar);
     __syncwarp();
@@ -938,6 +945,9 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     iv.ops = sm_ops; iv.len = sm_len; iv.rem = sm_rem; iv.si = si;
     int staged = -1;
     uint32_t phase = 0;
+    // Static strided tiles; the env after the current one is known one iteration ahead, which is what
+    // the TMA prefetch needs.  (A per-warp ticket counter for dynamic balancing was measured and was
+    // not faster: 109.4 vs 107.4 us per launch, profiles/r01_notes.md.)
     int tile = a.tile_begin + (int)blockIdx.x;
     int env_next = jss_tile_env(p, tile, a.tile_end, warp);
     int act_next = 0;
@@ -980,7 +990,11 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
             if (lane == 0) a.actions_out[env] = nxt;
         }
         if (changed) {
-            env_store<KJ>(p, iv, env, lane, s);
+            // new state -> shared staging -> one bulk store (every word of the block is rewritten)
+            env_store_to<KJ>(p, iv, state_out, lane, s);
+            jss_fence_async_smem();
+            __syncwarp();
+            if (lane == 0) jss_bulk_store(p.state + (size_t)env * p.block_words, state_out_sa, blk_bytes);
             env_emit_all<KJ, true>(p, iv, s, env, lane, scratch, raw, scratch_sa);
         } else if (s.flags != flags_in) {                // only the sticky error bit changed
             if (lane == 0) {
