@@ -11,6 +11,7 @@ __version__ = "0.1.0"
 from .env import JssEnv  # noqa: F401
 from .vec_env import JssVecEnv  # noqa: F401
 from . import dispatching  # noqa: F401
+from .gym_vector import JssGymVectorEnv  # noqa: F401
 from .instances import bundled_names, load_instance, parse_taillard, write_taillard  # noqa: F401
 
 try:  # same id / entry-point style as JSSEnv/__init__.py:6-9 (gymnasium is optional here)

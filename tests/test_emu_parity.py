@@ -89,3 +89,23 @@ def test_emu_step_sample_fused(rule):
 
 def test_emu_host_pipeline():
     pc.check_host_pipeline(make_env, "ta01", seed=3)
+
+
+def test_emu_gym_vector_adapter_autoreset():
+    """next-step autoreset through the VectorEnv-style adapter: the step after `done` returns the reset obs."""
+    from jssenv_b200 import JssGymVectorEnv
+    env = JssGymVectorEnv(3, {"instance_path": "ta01"}, to_numpy=True, seed=5)
+    obs, info = env.reset()
+    assert obs["real_obs"].shape == (3, 15, 7) and obs["action_mask"][:, :15].all() and info == {}
+    seen_done = np.zeros(3, bool)
+    for k in range(600):
+        acts = np.array([np.flatnonzero(m)[0] if m.any() else 0 for m in obs["action_mask"]], np.int32)
+        prev_done = seen_done.copy()
+        obs, rew, done, trunc, info = env.step(acts)
+        for i in np.flatnonzero(prev_done & ~done):     # the transition right after a terminal one = reset
+            assert obs["action_mask"][i, :15].all() and rew[i] == 0.0 and obs["real_obs"][i, :, 1:].max() == 0.0
+        seen_done = done.copy()
+        if env.vec.episode_count.min() >= 2:
+            break
+    assert int(env.vec.episode_count.min()) >= 2
+    env.close()
