@@ -437,3 +437,73 @@ def check_host_pipeline(make_env, name, seed):
         assert np.array_equal(env.host_wait_obs(previous=True), obs_prev_expected), k
         a = nxt
     return env
+
+
+def synthetic_instance(J, M, seed, max_dur=99, permutation=True):
+    """Random instance; with permutation=False a job may visit a machine several times / skip others
+    (the reference accepts that: it only requires M (machine, duration) pairs per job)."""
+    rng = np.random.default_rng(seed)
+    if permutation:
+        machine = np.stack([rng.permutation(M) for _ in range(J)]).astype(np.int32)
+    else:
+        machine = rng.integers(0, M, size=(J, M)).astype(np.int32)
+    duration = rng.integers(1, max_dur + 1, size=(J, M)).astype(np.int32)
+    return machine, duration
+
+
+def check_synthetic_shapes(make_env, shapes, n_steps, seed):
+    """Edge shapes: kernel limits (J = 128, M = 32, duration 2047), partially filled lanes (J = 33, 65, 127),
+    tiny instances (J = 1, M = 2), non-permutation machine sequences -- each against the oracle."""
+    insts = [synthetic_instance(J, M, seed + k, md, perm) for k, (J, M, md, perm) in enumerate(shapes)]
+    env = make_env(len(insts), {"instance_paths": insts, "env_to_instance": list(range(len(insts)))})
+    oracles = [OracleEnv(m, d) for m, d in insts]
+    rng = np.random.default_rng(seed)
+    obs = env.reset()
+    for o in oracles:
+        o.reset()
+    alive = np.ones(len(insts), bool)
+    for i, o in enumerate(oracles):
+        compare_env_to_oracle(env, i, o, obs, ctx="reset")
+    for step in range(n_steps):
+        acts = np.full(len(insts), N.ACTION_SKIP, np.int32)
+        for i, o in enumerate(oracles):
+            if alive[i]:
+                legal = np.flatnonzero(o.legal_actions)
+                acts[i] = int(legal[rng.integers(len(legal))])
+        obs, reward, done, _, _ = env.step(acts)
+        reward, done, raw = _np(reward), _np(done), _np(env.reward_raw)
+        for i, o in enumerate(oracles):
+            if not alive[i]:
+                continue
+            _, r, d, _, _ = o.step(int(acts[i]))
+            compare_env_to_oracle(env, i, o, obs, (reward[i], r), (done[i], d), (raw[i], o.last_raw_reward),
+                                  ctx=f"shape {shapes[i]} step {step}")
+            alive[i] = not d
+        if step % 40 == 0:
+            compare_exported_state(env, oracles, alive, ctx=f"step {step}")
+        if not alive.any():
+            break
+    return env
+
+
+def check_abi_error_codes(make_env):
+    """jss_load_instances / jss_assign / jss_step argument validation (rc < 0 -> NativeError with a message)."""
+    import pytest
+    from jssenv_b200._native import NativeError
+    bad = [
+        (synthetic_instance(129, 4, 1), "exceeds"),                      # J > JSS_MAX_JOBS
+        (synthetic_instance(4, 33, 1), "exceeds"),                       # M > JSS_MAX_MACHINES
+        ((np.zeros((3, 1), np.int32), np.ones((3, 1), np.int32)), "machines"),   # "We need at least 2 machines"
+    ]
+    for inst, msg in bad:
+        with pytest.raises((NativeError, ValueError), match=msg):
+            make_env(2, {"instance_path": inst})
+    m, d = synthetic_instance(5, 3, 2)
+    d0 = d.copy(); d0[1, 1] = 0
+    with pytest.raises(NativeError, match="duration"):                   # zero-length op (see DESIGN.md section 1)
+        make_env(2, {"instance_path": (m, d0)})
+    d1 = d.copy(); d1[0, 0] = 2048
+    with pytest.raises(NativeError, match="duration"):
+        make_env(2, {"instance_path": (m, d1)})
+    with pytest.raises(NativeError, match="out of range"):
+        make_env(2, {"instance_paths": [(m, d)], "env_to_instance": [0, 1]})

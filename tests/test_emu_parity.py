@@ -109,3 +109,15 @@ def test_emu_gym_vector_adapter_autoreset():
             break
     assert int(env.vec.episode_count.min()) >= 2
     env.close()
+
+
+EDGE_SHAPES = [(1, 2, 9, True), (2, 2, 5, True), (33, 3, 30, True), (65, 5, 99, True), (127, 7, 50, True),
+               (128, 32, 2047, True), (32, 32, 200, True), (64, 20, 99, True), (17, 6, 40, False), (100, 20, 99, False)]
+
+
+def test_emu_edge_shapes_and_limits():
+    pc.check_synthetic_shapes(make_env, EDGE_SHAPES, n_steps=260, seed=100)
+
+
+def test_emu_abi_error_codes():
+    pc.check_abi_error_codes(make_env)

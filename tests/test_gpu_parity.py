@@ -218,3 +218,16 @@ def test_gpu_config5_mixed_ta01_ta80_rules():
 def test_gpu_host_pipeline():
     pc.check_host_pipeline(make_env, "ta01", seed=3)
     pc.check_host_pipeline(make_env, "ta80", seed=4)
+
+
+def test_gpu_edge_shapes_and_limits():
+    """Kernel limits and ragged shapes, full episodes: J = 1 .. 128, M = 2 .. 32, durations to 2047,
+    partially filled lanes, non-permutation machine sequences."""
+    shapes = [(1, 2, 9, True), (2, 2, 5, True), (33, 3, 30, True), (65, 5, 99, True), (127, 7, 50, True),
+              (128, 32, 2047, True), (32, 32, 200, True), (64, 20, 99, True), (17, 6, 40, False), (100, 20, 99, False),
+              (128, 32, 99, False), (96, 31, 700, True)]
+    pc.check_synthetic_shapes(make_env, shapes, n_steps=9000, seed=100)
+
+
+def test_gpu_abi_error_codes():
+    pc.check_abi_error_codes(make_env)
