@@ -107,8 +107,16 @@ size_t smem_bytes(const JssSmemLayout &sl) {
     return sizeof(SmInst) + (size_t)sl.ops_elems * 2 + (size_t)sl.len_elems * 4 + (size_t)sl.rem_elems * 2 +
            (size_t)JSS_WARPS_PER_CTA * sl.scratch_words * 4;
 }
-template <int KJ, int SAMPLE>
-int launch_step_variant(jss_t *h, const JssLaunch &a, bool want_rem, cudaStream_t st) {
+template <int KJ, int SAMPLE, bool UNI>
+int launch_step_variant(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStream_t st) {
+    JssLaunch a = a_in;
+    if (UNI) {
+        const JssInstDesc &d = h->descs[h->p.uniform_inst];
+        SmInst &u = a.uni;
+        u.J = d.J; u.M = d.M; u.max_time_op = d.max_time_op; u.max_time_jobs = d.max_time_jobs; u.sum_op = d.sum_op;
+        u.f_mto = (float)d.max_time_op; u.f_mtj = (float)d.max_time_jobs; u.f_sop = (float)d.sum_op; u.f_M = (float)d.M;
+        u.r_mto = d.r_mto; u.r_mtj = d.r_mtj; u.r_sop = d.r_sop; u.r_M = d.r_M;
+    }
     const int n_tiles = a.tile_end - a.tile_begin;
     JssSmemLayout sl = want_rem ? h->sl_rem : h->sl_norem;
     sl.statein_words = h->p.block_words;
@@ -118,7 +126,7 @@ int launch_step_variant(jss_t *h, const JssLaunch &a, bool want_rem, cudaStream_
     sl.off_scratch = 16 + sl.statein_words * 4;
     sl.warp_stride = sl.off_scratch + sl.scratch_words * 4 + sl.statein_words * 4;   // + state-out staging
     const size_t smem = (size_t)sl.off_warp0 + (size_t)JSS_WARPS_PER_CTA * sl.warp_stride;
-    auto kern = jss_step_kernel<KJ, SAMPLE>;
+    auto kern = jss_step_kernel<KJ, SAMPLE, UNI>;
     int &grid = h->step_grid[(KJ == 1 ? 0 : (KJ == 2 ? 1 : 2)) * 4 + SAMPLE + (want_rem ? 1 : 0)];
     if (grid == 0) {                                     // once per handle: opt-in smem + occupancy
         if (smem > 48 * 1024)
@@ -136,9 +144,15 @@ int launch_step_variant(jss_t *h, const JssLaunch &a, bool want_rem, cudaStream_
 
 template <int KJ>
 int launch_step(jss_t *h, const JssLaunch &a, cudaStream_t st) {
-    if (a.actions_out == nullptr) return launch_step_variant<KJ, 0>(h, a, false, st);
-    if (a.rule == JSS_RULE_RANDOM) return launch_step_variant<KJ, 1>(h, a, false, st);
-    return launch_step_variant<KJ, 2>(h, a, a.rule == JSS_RULE_MWR || a.rule == JSS_RULE_LWR || a.rule == JSS_RULE_CR, st);
+    const bool rem = a.rule == JSS_RULE_MWR || a.rule == JSS_RULE_LWR || a.rule == JSS_RULE_CR;
+    if (h->p.uniform_inst >= 0) {
+        if (a.actions_out == nullptr) return launch_step_variant<KJ, 0, true>(h, a, false, st);
+        if (a.rule == JSS_RULE_RANDOM) return launch_step_variant<KJ, 1, true>(h, a, false, st);
+        return launch_step_variant<KJ, 2, true>(h, a, rem, st);
+    }
+    if (a.actions_out == nullptr) return launch_step_variant<KJ, 0, false>(h, a, false, st);
+    if (a.rule == JSS_RULE_RANDOM) return launch_step_variant<KJ, 1, false>(h, a, false, st);
+    return launch_step_variant<KJ, 2, false>(h, a, rem, st);
 }
 
 template <int KJ, int MODE>

@@ -37,14 +37,6 @@
 #define JSS_DEV __device__ __forceinline__
 #endif
 
-// Per-instance scalars live in shared memory next to the staged tables (CTA-uniform, re-read
-// with cheap broadcast LDS instead of pinning ~14 registers per thread).
-struct SmInst {
-    int J, M, max_time_op, max_time_jobs, sum_op;
-    float f_mto, f_mtj, f_sop, f_M;       // the divisors as floats ...
-    float r_mto, r_mtj, r_sop, r_M;       // ... and their correctly rounded reciprocals
-    int pad_[3];
-};
 struct InstView {  // instance tables staged in shared memory
     const uint16_t *ops;
     const int32_t *len;
@@ -920,7 +912,9 @@ jss_env_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
 // while the current env is simulated, and the observation staging buffer that leaves by bulk store.
 // SAMPLE = true additionally picks every env's NEXT action (masked-uniform sampler or a
 // dispatching rule) from the freshly computed state, so a policy-driven loop is one launch per step.
-template <int KJ, int SAMPLE>   // 0: step only, 1: + masked-uniform sampler, 2: + any dispatching rule
+// UNI = true (every env runs the same instance): the per-instance scalars are read from the kernel
+// parameters (constant bank operands) instead of shared memory.
+template <int KJ, int SAMPLE, bool UNI>   // SAMPLE 0: step only, 1: + masked-uniform sampler, 2: + any dispatching rule
 __global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, JSS_MIN_CTAS)
 jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JSS_SMEM_DECL(jss_smem);
@@ -942,7 +936,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     if (lane == 0) jss_mbar_init(mbar);
     __syncwarp();
     InstView iv;
-    iv.ops = sm_ops; iv.len = sm_len; iv.rem = sm_rem; iv.si = si;
+    iv.ops = sm_ops; iv.len = sm_len; iv.rem = sm_rem; iv.si = UNI ? &a.uni : si;
     int staged = -1;
     uint32_t phase = 0;
     // Static strided tiles; the env after the current one is known one iteration ahead, which is what

@@ -67,6 +67,15 @@ struct JssParams {
     uint8_t *x_legal, *x_blocked;
 };
 
+// Per-instance scalars: staged in shared memory next to the tables (CTA-uniform, re-read with cheap
+// broadcast LDS instead of pinning ~14 registers per thread), or -- uniform batches -- passed in the
+// kernel parameters so they become constant-bank operands.
+struct SmInst {
+    int J, M, max_time_op, max_time_jobs, sum_op;
+    float f_mto, f_mtj, f_sop, f_M;       // the divisors as floats ...
+    float r_mto, r_mtj, r_sop, r_M;       // ... and their correctly rounded reciprocals
+    int pad_[3];
+};
 struct JssLaunch {           // per-launch arguments
     int32_t tile_begin, tile_end;
     int32_t mode;            // JSS_MODE_*
@@ -75,6 +84,7 @@ struct JssLaunch {           // per-launch arguments
     const int32_t *actions;  // step
     int32_t *actions_out;    // policy
     const uint8_t *env_mask; // reset / import
+    SmInst uni;              // scalars of the single instance of a uniform batch (step kernel, UNI = true)
 };
 
 #define JSS_MODE_RESET 0
