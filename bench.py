@@ -137,14 +137,17 @@ def cpu_reference_leg(instance, budget_s, threads=None):
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (C oracle port, the Python reference cannot travel to the
+    GPU box) on all usable host threads; each "step" is one bounded wall-time window of the workload."""
     if rank != 0:
         return
     J, M = 100, 20
-    vals = []
-    sample = ""
-    for k in range(args.warmup_ref + args.steps_ref):
-        v, P, sample = cpu_reference_leg("ta80", args.cpu_seconds)
-        if k >= args.warmup_ref:
+    windows = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    vals, sample, P = [], "", 1
+    for k in range(warm + windows):
+        v, P, sample = cpu_reference_leg("ta80", 2.0 if k < warm else args.cpu_seconds)
+        if k >= warm:
             vals.append(v)
     value = sum(vals) / len(vals)
     print(json.dumps({
@@ -152,7 +155,9 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": "ta80 (100x20) masked-random, auto-reset, CPU oracle port of the reference step()",
-                   "envs": P, "bytes_per_env_step": b_alg(J, M)},
+                   "envs": P, "bytes_per_env_step": b_alg(J, M), "timed_windows": windows,
+                   "window_seconds": args.cpu_seconds,
+                   "python_reference_steps_per_s_per_core": 4378},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": P, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -168,8 +173,6 @@ def main():
     ap.add_argument("--instance", default="ta80")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--steps-ref", type=int, default=1)
-    ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -300,7 +303,8 @@ def main():
             out["e2e"] = e2e
         if not args.no_cpu:
             v, P, sample = cpu_reference_leg(args.instance, args.cpu_seconds)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": P, "kind": "port", "sample": sample}
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": P, "kind": "port", "sample": sample,
+                                   "python_reference_steps_per_s_per_core": 4378}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

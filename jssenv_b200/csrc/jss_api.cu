@@ -59,7 +59,6 @@ struct jss_handle {
     std::vector<int32_t> env_inst;
 
     // host-buffer stepping
-    int32_t *pin_actions = nullptr;
     int32_t *dev_actions = nullptr;
     float *obs_staging = nullptr;                  // pipelined mode: device copy the D2H engine reads from
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
@@ -255,7 +254,6 @@ void jss_destroy(jss_t *h) {
         cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy);
     }
     for (void *ptr : h->allocs) cudaFree(ptr);
-    if (h->pin_actions) cudaFreeHost(h->pin_actions);
     delete h;
 }
 

@@ -74,7 +74,6 @@ JSS_DEV uint32_t jss_bit(uint32_t mask, uint32_t pos) {
 }
 JSS_DEV uint32_t jss_op_m(uint32_t op) { return op >> JSS_OP_SHIFT; }
 JSS_DEV int jss_op_d(uint32_t op) { return (int)(op & JSS_OP_DMASK); }
-JSS_DEV uint32_t jss_op_at(const InstView &iv, int j, int ts) { return iv.ops[j * iv.si->M + ts]; }
 template <int KJ>
 JSS_DEV constexpr uint32_t jss_legal_mask() { return (1u << KJ) - 1u; }
 
@@ -583,12 +582,15 @@ JSS_DEV bool env_step(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, in
     // ONE inlined copy of the time advance serves the three callers: the raw hook (exactly one
     // advance), the no-op (:429-430, at least one) and the job branch (:469-470, zero or more)
     bool force = wait;
-    while (force || (!__any_sync(JSS_FULL, (s.lb & LM) != 0u) && __any_sync(JSS_FULL, s.tuam > 0))) {
+    uint32_t st;                                         // bit 0: some job is legal, bit 1: some event is pending
+    for (;;) {
+        st = __reduce_or_sync(JSS_FULL, ((s.lb & LM) != 0u ? 1u : 0u) | (s.tuam > 0 ? 2u : 0u));
+        if (!(force || st == 2u)) break;                 // advance while nothing is legal and an event is pending
         holes += env_advance<KJ>(iv, s, lane);
         force = false;
         if (action == JSS_ACTION_ADVANCE) { raw_reward = -holes; return true; }   // heuristics / _is_done do NOT run
     }
-    if (action == iv.si->J && !__any_sync(JSS_FULL, (s.lb & LM) != 0u))
+    if (action == iv.si->J && !(st & 1u))
         s.flags |= JSS_FLAG_ERROR;                       // the reference raises here (queue ran empty)
     raw_reward = gain - holes;
     env_prioritize<KJ>(iv, s, lane);                     // :432 / :471
@@ -852,8 +854,9 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
     }
 }
 
+template <bool UNI = false>
 JSS_DEV void jss_tile_desc(const JssParams &p, int tile, int &first, int &inst, int &count) {
-    if (p.uniform_inst >= 0) {           // one instance, identity order: no descriptor loads
+    if (UNI || p.uniform_inst >= 0) {    // one instance, identity order: no descriptor loads
         first = tile * JSS_WARPS_PER_CTA;
         inst = p.uniform_inst;
         count = min(JSS_WARPS_PER_CTA, p.n_envs - first);
@@ -862,7 +865,12 @@ JSS_DEV void jss_tile_desc(const JssParams &p, int tile, int &first, int &inst, 
         first = td.first; inst = td.inst_count >> 8; count = td.inst_count & 255;
     }
 }
+template <bool UNI = false>
 JSS_DEV int jss_tile_env(const JssParams &p, int tile, int tile_end, int warp) {
+    if (UNI) {                           // env = 8 * tile + warp, nothing to load
+        const int e = tile * JSS_WARPS_PER_CTA + warp;
+        return (tile < tile_end && e < p.n_envs) ? e : -1;
+    }
     if (tile >= tile_end) return -1;
     int first, inst, count;
     jss_tile_desc(p, tile, first, inst, count);
@@ -943,7 +951,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     // the TMA prefetch needs.  (A per-warp ticket counter for dynamic balancing was measured and was
     // not faster: 109.4 vs 107.4 us per launch, profiles/r01_notes.md.)
     int tile = a.tile_begin + (int)blockIdx.x;
-    int env_next = jss_tile_env(p, tile, a.tile_end, warp);
+    int env_next = jss_tile_env<UNI>(p, tile, a.tile_end, warp);
     int act_next = 0;
     if (env_next >= 0) {
         if (lane == 0) jss_bulk_load(state_sa, p.state + (size_t)env_next * p.block_words, blk_bytes, mbar);
@@ -951,7 +959,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     }
     for (; tile < a.tile_end; tile += (int)gridDim.x) {
         int first, inst, count;
-        jss_tile_desc(p, tile, first, inst, count);
+        jss_tile_desc<UNI>(p, tile, first, inst, count);
         if (inst != staged) {                            // CTA-uniform
             __syncthreads();
             jss_stage_instance(p, p.inst[inst], si, sm_ops, sm_len, sm_rem, SAMPLE == 2 && sl.rem_elems > 0);
@@ -959,7 +967,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
             __syncthreads();
         }
         const int env = env_next, action = act_next;
-        env_next = jss_tile_env(p, tile + (int)gridDim.x, a.tile_end, warp);
+        env_next = jss_tile_env<UNI>(p, tile + (int)gridDim.x, a.tile_end, warp);
         EnvRegs<KJ> s;
         if (env >= 0) {
             jss_mbar_wait(mbar, phase);                  // this env's block has landed in shared memory
