@@ -90,11 +90,9 @@ class JssEnv(_gym.Env if _gym is not None else object):
         safe = np.minimum(todo, M - 1)
         ar = np.arange(J)
         self.needed_machine_jobs = np.where(unfinished, self.instance_matrix[ar, safe, 0], -1).astype(np.int64)
-        cur_d = self.instance_matrix[ar, safe, 1]
         # total_perform = t - total_idle until the job completes (then jobs_length)
         self.total_perform_op_time_jobs = np.where(
             unfinished, self.current_time_step - self.total_idle_time_jobs, self.jobs_length).astype(np.int64)
-        del cur_d
         ml = np.zeros(M, dtype=bool)
         ml[self.needed_machine_jobs[legal[:J]]] = True         # machine_legal == "some legal job needs it"
         self.machine_legal = ml
@@ -110,6 +108,15 @@ class JssEnv(_gym.Env if _gym is not None else object):
                           for e in self.next_time_step]
         self.solution = v.solution[0].cpu().numpy().astype(np.int64)
         self.state = v.real_obs[0].cpu().numpy().astype(np.float64)
+
+    def _raise_for_error(self, message):
+        """The device error bit is sticky; the facade turns it into the reference's IndexError once and
+        clears it (state re-imported unchanged) so the env stays usable if the caller catches it."""
+        snap = self._vec.export_state()
+        snap["flags"].bitwise_and_(~((N.FLAG_ERROR) << 8))
+        self._vec.import_state(snap)
+        self._pull()
+        raise IndexError(message)
 
     def _get_current_state_representation(self):
         return {"real_obs": self.state, "action_mask": self.legal_actions}
@@ -133,7 +140,7 @@ class JssEnv(_gym.Env if _gym is not None else object):
         if self._flags & N.FLAG_ERROR:
             # the reference raises IndexError here (jss_env.py:444 / :517) or silently corrupts
             # its counters (illegal job action); the device env sets the sticky error bit
-            raise IndexError(f"illegal action {a} for the current state (error bit set)")
+            self._raise_for_error(f"illegal action {a} for the current state")
         reward = float(self._vec.reward[0])
         done = bool(self._vec.done[0])
         if done:                                               # jss_env.py:649-652
@@ -146,7 +153,7 @@ class JssEnv(_gym.Env if _gym is not None else object):
         self._vec.step(np.array([N.ACTION_ADVANCE], dtype=np.int32))
         self._pull()
         if self._flags & N.FLAG_ERROR:
-            raise IndexError("pop from empty list")           # what the reference raises (jss_env.py:517)
+            self._raise_for_error("pop from empty list")      # what the reference raises (jss_env.py:517)
         return -int(self._vec.reward_raw[0])
 
     def rule_action(self, rule: str):

@@ -9,7 +9,7 @@ memory owned by the native library), the no-op is action index ``J``, actions ar
 not validated beyond setting a per-env error bit, and ``truncated`` is always False.
 """
 import ctypes
-from typing import Any, Dict, List, Optional, Sequence, Union
+from typing import Any, Dict, Optional, Union
 
 import numpy as np
 

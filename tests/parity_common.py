@@ -507,3 +507,27 @@ def check_abi_error_codes(make_env):
         make_env(2, {"instance_path": (m, d1)})
     with pytest.raises(NativeError, match="out of range"):
         make_env(2, {"instance_paths": [(m, d)], "env_to_instance": [0, 1]})
+
+
+def check_facade_errors():
+    """Reference exceptions through the facade: IndexError once, env unchanged and usable afterwards."""
+    import pytest
+    env = JssEnv({"instance_path": "ta01"})
+    o = OracleEnv(*load_instance("ta01"))
+    env.reset(); o.reset()
+    with pytest.raises(IndexError):            # no-op with an empty event queue (jss_env.py:517)
+        env.step(env.jobs)
+    with pytest.raises(IndexError):            # raw advance with an empty event queue
+        env.increase_time_step()
+    obs, r, done, _, _ = env.step(2)
+    o.step(2)
+    assert np.array_equal(env.legal_actions, o.legal_actions) and env.current_time_step == o.current_time_step
+    with pytest.raises(IndexError):            # job 2 is running now: not legal
+        env.step(2)
+    with pytest.raises(IndexError):
+        env.step(env.jobs + 5)
+    obs, r, done, _, _ = env.step(4)           # still usable, still in lock-step with the oracle
+    oo, r2, d2, _, _ = o.step(4)
+    assert np.array_equal(obs["action_mask"], oo["action_mask"]) and rew_close(r, r2) and done == d2
+    assert env.render() is not None and len(env.render()) == 2
+    env.close()

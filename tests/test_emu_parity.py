@@ -121,3 +121,14 @@ def test_emu_edge_shapes_and_limits():
 
 def test_emu_abi_error_codes():
     pc.check_abi_error_codes(make_env)
+
+
+@pytest.mark.parametrize("rule", ["RANDOM", "CR", "FIFO"])
+def test_emu_step_sample_fused_uniform_batch(rule):
+    """Uniform batches take the kernel variant that reads the instance scalars from kernel parameters."""
+    pc.check_step_sample(make_env, ["ta80"] * 3, rule, n_steps=200, seed=13)
+    pc.check_step_sample(make_env, ["ta01"] * 9, rule, n_steps=200, seed=14)
+
+
+def test_emu_facade_errors():
+    pc.check_facade_errors()

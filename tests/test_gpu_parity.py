@@ -231,3 +231,14 @@ def test_gpu_edge_shapes_and_limits():
 
 def test_gpu_abi_error_codes():
     pc.check_abi_error_codes(make_env)
+
+
+@pytest.mark.parametrize("rule", ["RANDOM", "CR", "FIFO"])
+def test_gpu_step_sample_fused_uniform_batch(rule):
+    """Uniform batches take the kernel variant that reads the instance scalars from kernel parameters."""
+    pc.check_step_sample(make_env, ["ta80"] * 3, rule, n_steps=2600, seed=13)
+    pc.check_step_sample(make_env, ["ta01"] * 9, rule, n_steps=600, seed=14)
+
+
+def test_gpu_facade_errors():
+    pc.check_facade_errors()
