@@ -422,6 +422,12 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
                 ts += 1;
             }
         }
+        // the reference returns as soon as machine_next covers every legal machine (:357 / :395);
+        // about half of the pass-2 runs end "legal", most of them after the first job slot
+        if (i + 1 < KJ && ML != 0u && __reduce_or_sync(JSS_FULL, want) == ML) {
+            __syncwarp();                               // hz aliases the obs staging buffer
+            return true;
+        }
     }
     want = __reduce_or_sync(JSS_FULL, want);
     __syncwarp();                                       // hz aliases the obs staging buffer
