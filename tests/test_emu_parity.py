@@ -132,3 +132,7 @@ def test_emu_step_sample_fused_uniform_batch(rule):
 
 def test_emu_facade_errors():
     pc.check_facade_errors()
+
+
+def test_emu_dispatching_api():
+    pc.check_dispatching_api(make_env)

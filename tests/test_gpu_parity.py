@@ -242,3 +242,7 @@ def test_gpu_step_sample_fused_uniform_batch(rule):
 
 def test_gpu_facade_errors():
     pc.check_facade_errors()
+
+
+def test_gpu_dispatching_api():
+    pc.check_dispatching_api(make_env)
