@@ -956,14 +956,22 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     // Static strided tiles; the env after the current one is known one iteration ahead, which is what
     // the TMA prefetch needs.  (A per-warp ticket counter for dynamic balancing was measured and was
     // not faster: 109.4 vs 107.4 us per launch, profiles/r01_notes.md.)
-    int tile = a.tile_begin + (int)blockIdx.x;
-    int env_next = jss_tile_env<UNI>(p, tile, a.tile_end, warp);
+    // Uniform batches: tiles strided over the CTAs.  Mixed batches: each CTA owns a CONTIGUOUS range of
+    // the (instance-sorted) tiles, so it re-stages instance tables once or twice instead of per tile.
+    int tile, tile_end, tile_step;
+    if (UNI) {
+        tile = a.tile_begin + (int)blockIdx.x; tile_end = a.tile_end; tile_step = (int)gridDim.x;
+    } else {
+        const int per = (a.tile_end - a.tile_begin + (int)gridDim.x - 1) / (int)gridDim.x;
+        tile = a.tile_begin + (int)blockIdx.x * per; tile_end = min(tile + per, a.tile_end); tile_step = 1;
+    }
+    int env_next = jss_tile_env<UNI>(p, tile, tile_end, warp);
     int act_next = 0;
     if (env_next >= 0) {
         if (lane == 0) jss_bulk_load(state_sa, p.state + (size_t)env_next * p.block_words, blk_bytes, mbar);
         act_next = a.actions[env_next];
     }
-    for (; tile < a.tile_end; tile += (int)gridDim.x) {
+    for (; tile < tile_end; tile += tile_step) {
         int first, inst, count;
         jss_tile_desc<UNI>(p, tile, first, inst, count);
         if (inst != staged) {                            // CTA-uniform
@@ -973,7 +981,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
             __syncthreads();
         }
         const int env = env_next, action = act_next;
-        env_next = jss_tile_env<UNI>(p, tile + (int)gridDim.x, a.tile_end, warp);
+        env_next = jss_tile_env<UNI>(p, tile + tile_step, tile_end, warp);
         EnvRegs<KJ> s;
         if (env >= 0) {
             jss_mbar_wait(mbar, phase);                  // this env's block has landed in shared memory
