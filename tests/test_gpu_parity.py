@@ -246,3 +246,25 @@ def test_gpu_facade_errors():
 
 def test_gpu_dispatching_api():
     pc.check_dispatching_api(make_env)
+
+
+def test_gpu_soak_auto_reset_full_size():
+    """N = 65 536 ta80, 7 000 fused step+sample launches with auto-reset (about three episodes per env):
+    no error bits, every finished episode satisfies sum(raw reward) = 2*sum_op - M*makespan, statistics agree."""
+    n = 65536
+    env = make_env(n, {"instance_path": "ta80"}, seed=2024, auto_reset=True)
+    env.reset()
+    acts = env.policy("RANDOM").clone()
+    sum_op, M = int(env.instance_scalars[0, 2]), env.machines
+    for k in range(7000):
+        *_, acts = env.step_sample(acts, "RANDOM")
+        if k % 1000 == 999:
+            mk, ret, cnt = env.last_makespan.long(), env.last_return.long(), env.episode_count
+            fin = cnt > 0
+            assert bool((ret[fin] == 2 * sum_op - M * mk[fin]).all())
+    st = env.stats()
+    assert st["envs_error"] == 0 and int(env.episode_count.min()) >= 2
+    assert st["episodes"] == int(env.episode_count.sum()) and st["steps"] <= 7000 * n
+    assert 5800 <= st["min_makespan"] <= st["max_makespan"] <= 7500      # masked-random ta80 makespans
+    ro = env.real_obs
+    assert float(ro.min()) >= 0.0 and float(ro.max()) <= 1.0
