@@ -74,6 +74,7 @@ static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::collective(emu
 static inline void __syncthreads() { emu::collective(emu::OP_SYNCTHREADS, 0xffffffffu, 0, 0); }
 
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline float __fdiv_rn(float a, float b) { return a / b; }  // IEEE fp32 divide, round-to-nearest
