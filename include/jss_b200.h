@@ -200,12 +200,14 @@ int jss_step_host(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, flo
  * jss_host_wait(JSS_WAIT_MASK) blocks until mask/scalars of the latest begin have landed (enough
  * for a host policy to choose the next actions); JSS_WAIT_OBS until its observation has landed.
  * A new begin may follow WAIT_MASK while the previous observation is still streaming into ITS host
- * buffer (callers alternate two pinned observation buffers and call WAIT_OBS before reading one). */
+ * buffer (callers alternate two pinned observation buffers and call WAIT_OBS before reading one).
+ * The pipeline is ordered after the work already enqueued on `after_stream` (the caller's stream);
+ * call jss_host_wait(JSS_WAIT_OBS) before going back to the stream-ordered entry points. */
 #define JSS_WAIT_MASK 1
 #define JSS_WAIT_OBS 2       /* observation of the latest begin */
 #define JSS_WAIT_OBS_PREV 3  /* observation of the begin before the latest one */
 int jss_host_step_begin(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, float *obs_host,
-                        int32_t *scalars_host);
+                        int32_t *scalars_host, void *after_stream);
 int jss_host_wait(jss_t *h, int what);
 
 /* --- auxiliary ----------------------------------------------------------- */

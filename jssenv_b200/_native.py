@@ -65,7 +65,7 @@ def _declare(L):
     L.jss_step_sample.argtypes = [c_void_p, c_void_p, c_int, c_int, c_uint64, c_uint64, c_void_p, c_void_p]
     L.jss_rollout.argtypes = [c_void_p, c_int, c_uint64, c_uint64, c_int, c_int, c_void_p]
     L.jss_step_host.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
-    L.jss_host_step_begin.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.jss_host_step_begin.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.jss_host_wait.argtypes = [c_void_p, c_int]
     L.jss_stats.argtypes = [c_void_p, POINTER(c_int64), c_void_p]
     L.jss_export_state.argtypes = [c_void_p, c_void_p]

@@ -559,7 +559,7 @@ int jss_step_host(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, flo
 }
 
 int jss_host_step_begin(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, float *obs_host,
-                        int32_t *scalars_host) {
+                        int32_t *scalars_host, void *after_stream) {
     int rc = check_ready(h);
     if (rc) return rc;
     if (!actions_host) return fail(h, JSS_ERR_INVALID, "jss_host_step_begin: actions_host is NULL");
@@ -578,6 +578,9 @@ int jss_host_step_begin(jss_t *h, const int32_t *actions_host, uint8_t *mask_hos
         h->pipe_ready = true;
     }
     cudaStream_t sc = h->s_compute;
+    // order the pipeline after whatever the caller enqueued on its own stream (reset, device-side steps ...)
+    JSS_CUDA(h, cudaEventRecord(h->ev_staged, (cudaStream_t)after_stream));
+    JSS_CUDA(h, cudaStreamWaitEvent(sc, h->ev_staged, 0));
     JSS_CUDA(h, cudaMemcpyAsync(h->dev_actions, actions_host, N * 4, cudaMemcpyHostToDevice, sc));
     rc = jss_step(h, h->dev_actions, (void *)sc);
     if (rc) return rc;

@@ -226,7 +226,7 @@ class JssVecEnv:
         b["actions"].numpy()[:] = a                      # pinned copy: the H2D must not race with the caller's array
         rc = self._L.jss_host_step_begin(self._h, ctypes.c_void_p(b["actions"].data_ptr()),
                                          ctypes.c_void_p(b["mask"].data_ptr()), ctypes.c_void_p(b["obs"].data_ptr()),
-                                         ctypes.c_void_p(b["scalars"].data_ptr()))
+                                         ctypes.c_void_p(b["scalars"].data_ptr()), self._stream())
         N.check(self._h, rc, "jss_host_step_begin")
         return self._pipe_slot
 
