@@ -94,4 +94,6 @@ struct JssLaunch {           // per-launch arguments
 #define JSS_MODE_EXPORT 4
 #define JSS_MODE_IMPORT 5
 
+#ifndef JSS_WARPS_PER_CTA
 #define JSS_WARPS_PER_CTA 8
+#endif
