@@ -164,10 +164,15 @@ JSS_DEV void jss_st<4>(int32_t *p, const int (&o)[4]) {
 // last job) hold todo == M, i.e. they behave like finished jobs everywhere.
 template <int KJ>
 JSS_DEV void env_derive_ops(const InstView &iv, EnvRegs<KJ> &s, int lane) {
-    const int row = KJ * lane * iv.si->M;
+    const int M = iv.si->M;
+    // lanes past the last job read row 0 (any in-bounds row: their todo == M selects JSS_OP_NONE anyway)
+    const int row = (KJ * lane < iv.si->J) ? KJ * lane * M : 0;
 #pragma unroll
-    for (int i = 0; i < KJ; i++)
-        s.op[i] = (s.todo[i] < iv.si->M) ? (uint32_t)iv.ops[row + i * iv.si->M + s.todo[i]] : JSS_OP_NONE;
+    for (int i = 0; i < KJ; i++) {
+        // unconditional load of a clamped index + select: no divergent branch around the table lookup
+        const uint32_t o = iv.ops[row + i * M + min(s.todo[i], M - 1)];
+        s.op[i] = (s.todo[i] < M) ? o : JSS_OP_NONE;
+    }
 }
 
 template <int KJ>
@@ -278,36 +283,34 @@ JSS_DEV int env_advance(const InstView &iv, EnvRegs<KJ> &s, int lane) {
     const int hole = (int)__reduce_add_sync(JSS_FULL, (unsigned)((lane < iv.si->M && gap > 0) ? gap : 0));
     s.t += diff;
     const int row = KJ * lane * iv.si->M;
+    const int M = iv.si->M;
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
+        // branch-free form of the reference's three cases (select instructions instead of divergent
+        // branches): running (:529), running and finishing now (:550), waiting (:594); finished jobs
+        // (todo == M) fall through unchanged
         const int was = s.tufco[i];
-        bool finished = false;
-        if (was > 0) {                                    // running (:529)
-            const int left = was - diff;
-            s.tufco[i] = left > 0 ? left : 0;
-            if (left <= 0) {                              // op done (:550)
-                s.total_idle[i] += diff - was;
-                s.idle_last[i] = diff - was;
-                s.todo[i] += 1;
-                finished = true;
-                s.op[i] = (s.todo[i] < iv.si->M) ? (uint32_t)iv.ops[row + i * iv.si->M + s.todo[i]] : JSS_OP_NONE;
-            }
-        } else if (s.todo[i] < iv.si->M) {                    // waiting (:594)
-            s.total_idle[i] += diff;
-            s.idle_last[i] += diff;
-        }
+        const int left = was - diff;
+        const bool running = was > 0;
+        const bool finished = running && left <= 0;
+        const bool waiting = !running && s.todo[i] < M;
+        s.tufco[i] = left > 0 ? left : 0;                 // == max(0, was - diff); 0 stays 0
+        const int slack = diff - was;                     // idle part of the step for a job finishing now
+        s.total_idle[i] += finished ? slack : (waiting ? diff : 0);
+        s.idle_last[i] = finished ? slack : s.idle_last[i] + (waiting ? diff : 0);
+        s.todo[i] += finished ? 1 : 0;
+        if (finished) s.op[i] = (s.todo[i] < M) ? (uint32_t)iv.ops[row + i * M + s.todo[i]] : JSS_OP_NONE;
         // real_obs[:,4] uses the PRE-decrement countdown of the next machine (:569-578)
         const int tq = __shfl_sync(JSS_FULL, tuam_old, (int)(jss_op_m(s.op[i]) & 31u));
-        if (finished) {
-            const int w = tq - diff;
-            s.col4[i] = (s.op[i] != JSS_OP_NONE) ? (w > 0 ? w : 0) : iv.si->max_time_op;   // max_time_op encodes 1.0 (:586)
-        }
+        const int w = tq - diff;
+        const int c4 = (s.op[i] != JSS_OP_NONE) ? (w > 0 ? w : 0) : iv.si->max_time_op;   // max_time_op encodes 1.0 (:586)
+        s.col4[i] = finished ? c4 : s.col4[i];
     }
     s.tuam = gap < 0 ? -gap : 0;
     const uint32_t free_m = __ballot_sync(JSS_FULL, lane < iv.si->M && s.tuam == 0);
 #pragma unroll
-    for (int i = 0; i < KJ; i++)                          // legalisation (:616-634)
-        if (jss_bit(free_m, jss_op_m(s.op[i])) && !(s.lb & (16u << i))) s.lb |= 1u << i;
+    for (int i = 0; i < KJ; i++)                          // legalisation (:616-634): free machine and not blocked
+        s.lb |= (jss_bit(free_m, jss_op_m(s.op[i])) & ~(s.lb >> (4 + i)) & 1u) << i;
     return hole;
 }
 
@@ -316,8 +319,7 @@ template <int KJ>
 JSS_DEV uint32_t env_machine_legal(const EnvRegs<KJ> &s) {
     uint32_t mine = 0u;
 #pragma unroll
-    for (int i = 0; i < KJ; i++)
-        if (s.lb & (1u << i)) mine |= 1u << (jss_op_m(s.op[i]) & 31u);
+    for (int i = 0; i < KJ; i++) mine |= ((s.lb >> i) & 1u) << (jss_op_m(s.op[i]) & 31u);
     return __reduce_or_sync(JSS_FULL, mine);
 }
 
@@ -445,7 +447,8 @@ JSS_DEV void env_emit_obs(const JssParams &p, const InstView &iv, const EnvRegs<
             // total_perform_op_time_jobs == t - total_idle while the job is unfinished,
             // jobs_length[j] afterwards (every advance adds `difference` to exactly one of
             // the two counters until the job completes)
-            const int perf = (s.todo[i] < iv.si->M) ? s.t - s.total_idle[i] : iv.len[KJ * lane + i];
+            const int len = iv.len[KJ * lane + i];        // unconditional (in-bounds) load + select
+            const int perf = (s.todo[i] < iv.si->M) ? s.t - s.total_idle[i] : len;
             v[7 * i + 0] = (s.lb & (1u << i)) ? 1.0f : 0.0f;
             v[7 * i + 1] = jss_div((float)s.tufco[i], iv.si->f_mto, iv.si->r_mto);
             v[7 * i + 2] = jss_div((float)s.todo[i], iv.si->f_M, iv.si->r_M);
