@@ -575,13 +575,11 @@ JSS_DEV bool env_step(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, in
         if (opa == JSS_OP_NONE || !((bits_a >> ia) & 1u)) { s.flags |= JSS_FLAG_ERROR; return false; }
         const uint32_t m_a = jss_op_m(opa);
         gain = jss_op_d(opa);
-        if ((uint32_t)lane == m_a) s.tuam = gain;                    // :446
-        if (lane == la) {
+        s.tuam = ((uint32_t)lane == m_a) ? gain : s.tuam;            // :446
 #pragma unroll
-            for (int i = 0; i < KJ; i++) if (i == ia) s.tufco[i] = gain;   // :447
-            if (p.solution)                                           // :454
-                p.solution[((size_t)env * p.jobs_max + action) * p.machines_max + jss_sel<KJ>(s.todo, ia)] = s.t;
-        }
+        for (int i = 0; i < KJ; i++) s.tufco[i] = (lane == la && i == ia) ? gain : s.tufco[i];   // :447
+        if (p.solution && lane == la)                                 // :454
+            p.solution[((size_t)env * p.jobs_max + action) * p.machines_max + jss_sel<KJ>(s.todo, ia)] = s.t;
 #pragma unroll
         for (int i = 0; i < KJ; i++)
             // every job waiting for machine m_a: no longer legal (:455-461), no longer
@@ -641,11 +639,12 @@ JSS_DEV int env_select_action(const InstView &iv, const EnvRegs<KJ> &s, int lane
         const uint32_t before = incl - mine;
         const bool own = r >= before && r < incl;
         int act = 0;
-        if (own) {
-            uint32_t k = r - before;                     // k-th set slot of this lane
+        uint32_t k = r - before;                         // k-th set slot of this lane (meaningful if `own`)
 #pragma unroll
-            for (int i = 0; i < KJ; i++)
-                if (s.lb & (1u << i)) { if (k == 0) act = KJ * lane + i; k--; }
+        for (int i = 0; i < KJ; i++) {
+            const uint32_t bit = (s.lb >> i) & 1u;
+            act = (bit && k == 0u) ? KJ * lane + i : act;
+            k -= bit;
         }
         const uint32_t who = __ballot_sync(JSS_FULL, own);
         return __shfl_sync(JSS_FULL, act, __ffs((int)who) - 1);
