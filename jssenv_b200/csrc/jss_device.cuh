@@ -282,8 +282,8 @@ JSS_DEV int env_advance(const InstView &iv, EnvRegs<KJ> &s, int lane) {
     const int gap = diff - tuam_old;                      // > 0 only for machines idle before the event
     const int hole = (int)__reduce_add_sync(JSS_FULL, (unsigned)((lane < iv.si->M && gap > 0) ? gap : 0));
     s.t += diff;
-    const int row = KJ * lane * iv.si->M;
     const int M = iv.si->M;
+    const int row = (KJ * lane < iv.si->J) ? KJ * lane * M : 0;   // lanes past the last job: any in-bounds row
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
         // branch-free form of the reference's three cases (select instructions instead of divergent
@@ -299,7 +299,10 @@ JSS_DEV int env_advance(const InstView &iv, EnvRegs<KJ> &s, int lane) {
         s.total_idle[i] += finished ? slack : (waiting ? diff : 0);
         s.idle_last[i] = finished ? slack : s.idle_last[i] + (waiting ? diff : 0);
         s.todo[i] += finished ? 1 : 0;
-        if (finished) s.op[i] = (s.todo[i] < M) ? (uint32_t)iv.ops[row + i * M + s.todo[i]] : JSS_OP_NONE;
+        {   // next op of a job that just finished one: unconditional clamped lookup + selects (no branch)
+            const uint32_t o = iv.ops[row + i * M + min(s.todo[i], M - 1)];
+            s.op[i] = finished ? ((s.todo[i] < M) ? o : JSS_OP_NONE) : s.op[i];
+        }
         // real_obs[:,4] uses the PRE-decrement countdown of the next machine (:569-578)
         const int tq = __shfl_sync(JSS_FULL, tuam_old, (int)(jss_op_m(s.op[i]) & 31u));
         const int w = tq - diff;
@@ -383,20 +386,19 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
     while (lanes) {
         const int l = __ffs((int)lanes) - 1;
         lanes &= lanes - 1u;
-        const uint32_t bits = __shfl_sync(JSS_FULL, s.lb, l);
-#pragma unroll
-        for (int i = 0; i < KJ; i++) {
-            if (bits & (1u << i)) {                     // warp-uniform branch
-                const uint32_t o = __shfl_sync(JSS_FULL, s.op[i], l);
-                const int m = (int)jss_op_m(o);
-                const int end = s.t + jss_op_d(o);
-                if (end < next_event) return false;     // :314-315
-                int cur;
-                if (lm0 == m || lm0 < 0) { lm0 = m; h0 = min(h0, end); cur = h0; }
-                else if (lm1 == m || lm1 < 0) { lm1 = m; h1 = min(h1, end); cur = h1; }
-                else { lm2 = m; h2 = min(h2, end); cur = h2; }
-                maxh = max(maxh, cur);                  // :321
-            }
+        uint32_t bits = __shfl_sync(JSS_FULL, s.lb, l) & jss_legal_mask<KJ>();
+        while (bits) {                                  // warp-uniform: the legal jobs of lane l, ascending
+            const int i = __ffs((int)bits) - 1;
+            bits &= bits - 1u;
+            const uint32_t o = __shfl_sync(JSS_FULL, jss_sel<KJ>(s.op, i), l);
+            const int m = (int)jss_op_m(o);
+            const int end = s.t + jss_op_d(o);
+            if (end < next_event) return false;         // :314-315
+            int cur;
+            if (lm0 == m || lm0 < 0) { lm0 = m; h0 = min(h0, end); cur = h0; }
+            else if (lm1 == m || lm1 < 0) { lm1 = m; h1 = min(h1, end); cur = h1; }
+            else { lm2 = m; h2 = min(h2, end); cur = h2; }
+            maxh = max(maxh, cur);                      // :321
         }
     }
     // per-machine horizon table: finite only for machines that have a legal job, so the
