@@ -441,7 +441,8 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
 // ---- observation / mask / reward (jss_env.py:102-134, 483-493) ---------------------
 template <int KJ, bool BULK = false>
 JSS_DEV void env_emit_obs(const JssParams &p, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane,
-                          float *scratch, jss_saddr_t scratch_sa = jss_saddr_t()) {
+                          float *scratch, jss_saddr_t scratch_sa = jss_saddr_t(), void *st_dst = nullptr,
+                          jss_saddr_t st_sa = jss_saddr_t(), uint32_t st_bytes = 0u) {
     if (KJ * lane < iv.si->J) {
         float v[KJ * 7];
 #pragma unroll
@@ -475,14 +476,20 @@ JSS_DEV void env_emit_obs(const JssParams &p, const InstView &iv, const EnvRegs<
     }
     float *dst = p.obs + (size_t)env * p.jobs_max * 7;
     const int n = iv.si->J * 7;
-    if (BULK && (n & 3) == 0 && (p.jobs_max & 3) == 0) {
-        // ... and hand the env's J*7 floats to the TMA engine: one bulk copy shared -> global
+    if (BULK) {
+        // ONE proxy fence covers both staged buffers (new state block + observation rows), then lane 0
+        // hands them to the TMA engine: one bulk copy shared -> global each
         jss_fence_async_smem();          // make the generic-proxy writes visible to the async proxy
         __syncwarp();
-        if (lane == 0) jss_bulk_store(dst, scratch_sa, (uint32_t)n * 4u);
-        return;                          // the caller waits (wait_group.read) before reusing `scratch`
+        if (lane == 0) {
+            if (st_bytes) jss_bulk_store(st_dst, st_sa, st_bytes);
+            if ((n & 3) == 0 && (p.jobs_max & 3) == 0) jss_bulk_store(dst, scratch_sa, (uint32_t)n * 4u);
+        }
+        if ((n & 3) == 0 && (p.jobs_max & 3) == 0)
+            return;                      // the caller waits (wait_group.read) before reusing the staging buffers
+    } else {
+        __syncwarp();
     }
-    __syncwarp();
     // ... and stream the J*7 floats of the env out with fully coalesced stores
     int done_elems = 0;
     if ((p.jobs_max & 3) == 0) {
@@ -783,8 +790,9 @@ JSS_DEV void jss_stage_instance(const JssParams &p, const JssInstDesc &d, SmInst
 
 template <int KJ, bool BULK = false>
 JSS_DEV void env_emit_all(const JssParams &p, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane,
-                          float *scratch, int raw, jss_saddr_t scratch_sa = jss_saddr_t()) {
-    env_emit_obs<KJ, BULK>(p, iv, s, env, lane, scratch, scratch_sa);
+                          float *scratch, int raw, jss_saddr_t scratch_sa = jss_saddr_t(), void *st_dst = nullptr,
+                          jss_saddr_t st_sa = jss_saddr_t(), uint32_t st_bytes = 0u) {
+    env_emit_obs<KJ, BULK>(p, iv, s, env, lane, scratch, scratch_sa, st_dst, st_sa, st_bytes);
     env_emit_mask<KJ>(p, iv, s, env, lane, (s.flags & JSS_FLAG_NOOP_LEGAL) != 0u);
     env_emit_scalars<KJ>(p, iv, s, env, lane, raw);
 }
@@ -1012,10 +1020,8 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
         if (changed) {
             // new state -> shared staging -> one bulk store (every word of the block is rewritten)
             env_store_to<KJ>(p, iv, state_out, lane, s);
-            jss_fence_async_smem();
-            __syncwarp();
-            if (lane == 0) jss_bulk_store(p.state + (size_t)env * p.block_words, state_out_sa, blk_bytes);
-            env_emit_all<KJ, true>(p, iv, s, env, lane, scratch, raw, scratch_sa);
+            env_emit_all<KJ, true>(p, iv, s, env, lane, scratch, raw, scratch_sa,
+                                   p.state + (size_t)env * p.block_words, state_out_sa, blk_bytes);
         } else if (s.flags != flags_in) {                // only the sticky error bit changed
             if (lane == 0) {
                 p.state[(size_t)env * p.block_words + 5 * p.Jcap + p.Mcap + 8 + JSS_HDR_FLAGS] = (int32_t)s.flags;
