@@ -1,8 +1,9 @@
 // Counter-based RNG shared by the device policy kernels and the host helper
-// jss_host_masked_random().  One 32-bit draw per (seed, global env id, step
-// index): a splitmix64-style finaliser over a linear combination of the three
-// counters.  Stateless, so any env's action stream can be replayed on the host
-// (the CPU oracle restates the same function for its replays).
+// jss_host_masked_random().  One 32-bit draw per (seed, global env id, step index): the three
+// counters are folded to 32 bits, combined with odd multipliers and passed through the
+// murmur3 32-bit finaliser (~16 integer instructions on the GPU; a 64-bit splitmix variant cost
+// ~40).  Stateless, so any env's action stream can be replayed on the host (the CPU oracle
+// restates the same function for its replays).
 #pragma once
 #include <stdint.h>
 
@@ -12,12 +13,14 @@
 #define JSS_HD
 #endif
 
+JSS_HD static inline uint32_t jss_fold32(uint64_t v) { return (uint32_t)v ^ ((uint32_t)(v >> 32) * 0x7FEB352Du); }
+
 JSS_HD static inline uint32_t jss_hash3(uint64_t seed, uint64_t env, uint64_t ctr) {
-    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (env + 1) + 0xD1B54A32D192ED03ull * (ctr + 1);
-    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
-    z ^= z >> 27; z *= 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (uint32_t)(z >> 32);
+    uint32_t h = jss_fold32(seed) ^ (jss_fold32(env) * 0x9E3779B1u + 0x85EBCA77u) ^ (jss_fold32(ctr) * 0xC2B2AE3Du + 0x27D4EB2Fu);
+    h ^= h >> 16; h *= 0x85EBCA6Bu;
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
 }
 
 // index in [0, count) -- multiply-high, no modulo bias worth speaking of

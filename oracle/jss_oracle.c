@@ -532,12 +532,14 @@ const void *jsso_array(const jsso *o, int which) {
  * here so the oracle stays self-contained).  Returns the number of completed
  * episodes; *sum_makespan accumulates their makespans.
  * ------------------------------------------------------------------------ */
+static inline uint32_t jsso_fold32(uint64_t v) { return (uint32_t)v ^ ((uint32_t)(v >> 32) * 0x7FEB352Du); }
 static inline uint32_t jsso_hash3(uint64_t seed, uint64_t env, uint64_t ctr) {
-    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (env + 1) + 0xD1B54A32D192ED03ull * (ctr + 1);
-    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
-    z ^= z >> 27; z *= 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (uint32_t)(z >> 32);
+    uint32_t h = jsso_fold32(seed) ^ (jsso_fold32(env) * 0x9E3779B1u + 0x85EBCA77u) ^
+                 (jsso_fold32(ctr) * 0xC2B2AE3Du + 0x27D4EB2Fu);
+    h ^= h >> 16; h *= 0x85EBCA6Bu;
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
 }
 
 int jsso_masked_random_action(const jsso *o, uint64_t seed, uint64_t env, uint64_t ctr) {

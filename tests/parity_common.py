@@ -243,14 +243,23 @@ def check_policy_kernels(make_env, names, n_steps, seed):
             break
 
 
+def _hash3(seed, env, ctr):
+    """jssenv_b200/csrc/jss_rng.h restated for the tests."""
+    M32 = 0xFFFFFFFF
+
+    def fold(v):
+        return ((v & M32) ^ (((v >> 32) & M32) * 0x7FEB352D)) & M32
+
+    h = fold(seed) ^ ((fold(env) * 0x9E3779B1 + 0x85EBCA77) & M32) ^ ((fold(ctr) * 0xC2B2AE3D + 0x27D4EB2F) & M32)
+    h ^= h >> 16; h = (h * 0x85EBCA6B) & M32
+    h ^= h >> 13; h = (h * 0xC2B2AE35) & M32
+    h ^= h >> 16
+    return h
+
+
 def _coin_uniform(seed, env, ctr):
-    """u = hash3(seed, env, ctr) / 2^32 -- jssenv_b200/csrc/jss_rng.h restated for the test."""
-    M = (1 << 64) - 1
-    z = (seed + 0x9E3779B97F4A7C15 * (env + 1) + 0xD1B54A32D192ED03 * (ctr + 1)) & M
-    z ^= z >> 30; z = (z * 0xBF58476D1CE4E5B9) & M
-    z ^= z >> 27; z = (z * 0x94D049BB133111EB) & M
-    z ^= z >> 31
-    return (z >> 32) / 4294967296.0
+    """u = hash3(seed, env, ctr) / 2^32"""
+    return _hash3(seed, env, ctr) / 4294967296.0
 
 
 def check_rollout_matches_steps(make_env, names, rule, n_steps, seed):
