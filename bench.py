@@ -301,7 +301,7 @@ def main():
         }
         if e2e:
             out["e2e"] = e2e
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:               # the CPU baseline is reported at N = 1 only
             v, P, sample = cpu_reference_leg(args.instance, args.cpu_seconds)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": P, "kind": "port", "sample": sample,
                                    "python_reference_steps_per_s_per_core": 4378}
