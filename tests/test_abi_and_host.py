@@ -105,3 +105,22 @@ def test_stats_all_gather_world_size_2_gloo(tmp_path):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_markstein_division_is_exact_for_all_bundled_divisors(tmp_path):
+    """jss_div() (3 instructions) == IEEE fp32 division for every numerator/divisor pair the bundled instances
+    can produce (tools/check_div.c, exhaustive per divisor)."""
+    from jssenv_b200.instances import bundled_names, load_instance
+    exe = tmp_path / "check_div"
+    subprocess.check_call(["gcc", "-O1", "-ffp-contract=off", "-o", str(exe), os.path.join(ROOT, "tools", "check_div.c"), "-lm"])
+    args, seen = [], set()
+    for n in bundled_names():
+        m, d = load_instance(n)
+        for y in (int(d.max()), int(d.sum(1).max()), int(d.sum()), m.shape[1]):
+            if y not in seen:
+                seen.add(y)
+                args += [str(y), str(y)]
+    for y in range(1, 257):
+        args += [str(y), str(y)]
+    r = subprocess.run([str(exe)] + args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-400:]
