@@ -415,7 +415,9 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
     h->sl_norem.ops_elems = round_up(ops_max, 8);
     h->sl_norem.len_elems = round_up(jmax, 4);
     h->sl_norem.rem_elems = 0;
-    h->sl_norem.scratch_words = 7 * p.Jcap;
+    // observation staging (7 floats per job slot); env_check_no_op also keeps its 32-int per-warp
+    // machine-horizon table here, so never less than 32 words (tiny instances: 7 * Jcap < 32)
+    h->sl_norem.scratch_words = std::max(7 * p.Jcap, 32);
     h->sl_rem = h->sl_norem;
     h->sl_rem.rem_elems = round_up(rem_max, 8);
 

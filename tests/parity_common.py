@@ -265,8 +265,11 @@ def _coin_uniform(seed, env, ctr):
 def check_rollout_matches_steps(make_env, names, rule, n_steps, seed):
     """The fused rollout kernel == policy kernel + step kernel, transition for transition;
     and both == the oracle driven by the same counter RNG."""
-    uniq = sorted(set(names))
-    cfg = {"instance_paths": uniq, "env_to_instance": [uniq.index(n) for n in names]}
+    if isinstance(names[0], str):
+        uniq = sorted(set(names))
+        cfg = {"instance_paths": uniq, "env_to_instance": [uniq.index(n) for n in names]}
+    else:                                          # already-parsed (machine, duration) pairs, one per env
+        cfg = {"instance_paths": list(names), "env_to_instance": list(range(len(names)))}
     a_env = make_env(len(names), cfg, seed=seed, auto_reset=True)
     b_env = make_env(len(names), cfg, seed=seed, auto_reset=True)
     a_env.reset(); b_env.reset()
@@ -559,3 +562,40 @@ def check_dispatching_api(make_env):
     venv = make_env(4, {"instance_paths": ["ta01", "ta31"], "env_to_instance": [0, 0, 1, 1]}, seed=3)
     resb = compare_rules_batched(venv, rules=["FIFO", "LOR"])
     assert set(resb) == {"FIFO", "LOR"} and all(v["avg_makespan"] > 0 for v in resb.values())
+
+
+def check_tiny_uniform_batches(make_env, seed=50):
+    """Uniform batches of tiny instances (J <= 4, so Jcap = 4 and 7 * Jcap < 32): the per-warp scratch must
+    still hold _check_no_op's 32-entry horizon table (shared-memory overflow in the rollout kernel).
+    16 envs of one instance: fused rollout == policy + step kernels == oracle, transition for transition."""
+    for k, (J, M) in enumerate([(2, 2), (3, 4), (4, 3), (4, 32), (1, 2), (5, 5)]):
+        inst = synthetic_instance(J, M, seed + k, max_dur=30)
+        n = 16
+        cfg = {"instance_paths": [inst], "env_to_instance": [0] * n}
+        for rule in ("RANDOM", "SPT"):
+            a_env = make_env(n, cfg, seed=seed + k, auto_reset=True)
+            b_env = make_env(n, cfg, seed=seed + k, auto_reset=True)
+            a_env.reset(); b_env.reset()
+            n_steps = 6 * J * M + 7
+            a_env.rollout(rule, n_steps, write_obs=True)
+            oracles = [OracleEnv(*inst) for _ in range(n)]
+            done = [False] * n
+            for o in oracles:
+                o.reset()
+            for step in range(n_steps):
+                acts = b_env.policy(rule)
+                b_env.step(acts)
+                a_host = _np(acts)
+                for i, o in enumerate(oracles):
+                    if done[i]:
+                        o.reset(); done[i] = False
+                    else:
+                        exp = (o.masked_random_action(seed + k, i, step) if rule == "RANDOM"
+                               else o.rule_action(rule, _coin_uniform(seed + k, i, step))[0])
+                        assert a_host[i] == exp, (J, M, rule, step, i)
+                        _, _, done[i], _, _ = o.step(int(a_host[i]))
+                    compare_env_to_oracle(b_env, i, o, b_env._obs(), ctx=f"tiny {J}x{M} {rule} step {step}")
+            for name in ("action_mask", "real_obs", "reward", "reward_raw", "done", "current_time_step", "flags",
+                         "episode_count", "last_makespan", "last_return"):
+                assert np.array_equal(_np(getattr(a_env, name)), _np(getattr(b_env, name))), (J, M, rule, name)
+            assert a_env.stats() == b_env.stats() and a_env.stats()["envs_error"] == 0

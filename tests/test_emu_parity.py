@@ -136,3 +136,7 @@ def test_emu_facade_errors():
 
 def test_emu_dispatching_api():
     pc.check_dispatching_api(make_env)
+
+
+def test_emu_tiny_uniform_batches():
+    pc.check_tiny_uniform_batches(make_env)

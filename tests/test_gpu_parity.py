@@ -268,3 +268,7 @@ def test_gpu_soak_auto_reset_full_size():
     assert 5800 <= st["min_makespan"] <= st["max_makespan"] <= 7500      # masked-random ta80 makespans
     ro = env.real_obs
     assert float(ro.min()) >= 0.0 and float(ro.max()) <= 1.0
+
+
+def test_gpu_tiny_uniform_batches():
+    pc.check_tiny_uniform_batches(make_env)
