@@ -174,6 +174,11 @@ int jss_step(jss_t *h, const int32_t *actions_dev, void *stream);
 int jss_policy(jss_t *h, int rule, int coin_mode, uint64_t seed, uint64_t step_index,
                int32_t *actions_dev, void *stream);
 
+/* Replaces CriticalRatio.__init__(due_date_factor) (dispatching.py:337-349): the factor JSS_RULE_CR multiplies a
+ * job's total processing time with to get its due date (dispatching.py:357-360).  Default 1.5 like the reference;
+ * applies to every later jss_policy / jss_step_sample / jss_rollout with JSS_RULE_CR on this handle. */
+int jss_set_cr_due_date_factor(jss_t *h, double factor);
+
 /* jss_step() fused with jss_policy() for the NEXT decision: applies actions_dev, then
  * writes every env's next action (chosen by `rule` on the new state, RNG counter
  * `step_index`) to next_actions_dev, in one launch.  The two buffers may alias. */

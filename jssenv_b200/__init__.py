@@ -11,12 +11,21 @@ __version__ = "0.1.0"
 from .env import JssEnv  # noqa: F401
 from .vec_env import JssVecEnv  # noqa: F401
 from . import dispatching  # noqa: F401
-from .gym_vector import JssGymVectorEnv  # noqa: F401
+from .gym_vector import JssGymVectorEnv, create_env  # noqa: F401
 from .instances import bundled_names, load_instance, parse_taillard, write_taillard  # noqa: F401
 
-try:  # same id / entry-point style as JSSEnv/__init__.py:6-9 (gymnasium is optional here)
-    from gymnasium.envs.registration import register as _register
 
+
+def register_gymnasium() -> bool:
+    """Register the id the reference registers (JSSEnv/__init__.py:6-9: ``jss-v1``), pointing at the drop-in
+    facade, so ``gym.make('jss-v1', env_config={...})`` (README.md:46) keeps working.  Returns False when
+    gymnasium is not importable (it is optional: neither the build image nor the GPU box has it)."""
+    try:
+        from gymnasium.envs.registration import register as _register
+    except Exception:
+        return False
     _register(id="jss-v1", entry_point="jssenv_b200.env:JssEnv")
-except Exception:  # pragma: no cover - gymnasium absent in the build image
-    pass
+    return True
+
+
+register_gymnasium()

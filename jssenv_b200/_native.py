@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     "jss_abi_version", "jss_create", "jss_destroy", "jss_last_error", "jss_load_instances", "jss_assign",
     "jss_get_buffers", "jss_instance_scalars", "jss_reset", "jss_step", "jss_policy", "jss_rollout",
     "jss_step_host", "jss_host_step_begin", "jss_host_wait", "jss_step_sample", "jss_stats", "jss_export_state", "jss_import_state", "jss_host_masked_random",
-    "jss_launch_count",
+    "jss_launch_count", "jss_set_cr_due_date_factor",
 )
 
 
@@ -71,6 +71,8 @@ def _declare(L):
     L.jss_export_state.argtypes = [c_void_p, c_void_p]
     L.jss_import_state.argtypes = [c_void_p, c_void_p, c_void_p]
     L.jss_host_masked_random.argtypes = [c_void_p, c_int, c_int, c_int64, c_uint64, c_uint64, c_uint64, c_void_p]
+    L.jss_set_cr_due_date_factor.argtypes = [c_void_p, ctypes.c_double]
+    L.jss_set_cr_due_date_factor.restype = c_int
     L.jss_launch_count.argtypes = [c_void_p]
     L.jss_launch_count.restype = c_int64
     for name in ("jss_create", "jss_load_instances", "jss_assign", "jss_get_buffers", "jss_instance_scalars",

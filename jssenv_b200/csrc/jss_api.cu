@@ -40,6 +40,7 @@ struct jss_handle {
     int sm_count = 0;
     std::string err;
     int64_t launches = 0;
+    double cr_factor = 1.5;                        // CriticalRatio(due_date_factor), dispatching.py:337
 
     std::vector<HostInst> insts;
     std::vector<JssInstDesc> descs;
@@ -214,6 +215,12 @@ int jss_abi_version(void) { return JSS_ABI_VERSION; }
 const char *jss_last_error(const jss_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int64_t jss_launch_count(const jss_t *h) { return h ? h->launches : 0; }
+
+int jss_set_cr_due_date_factor(jss_t *h, double factor) {
+    if (!h || !(factor == factor)) return fail(h, JSS_ERR_INVALID, "jss_set_cr_due_date_factor: bad arguments");
+    h->cr_factor = factor;
+    return JSS_OK;
+}
 
 int jss_create(jss_t **out, int device, int n_envs, uint32_t flags, uint64_t env_id_base) {
     if (!out || n_envs <= 0) return fail(nullptr, JSS_ERR_INVALID, "jss_create: bad arguments");
@@ -509,7 +516,7 @@ int jss_step_sample(jss_t *h, const int32_t *actions_dev, int rule, int coin_mod
     a.mode = JSS_MODE_STEP;
     a.actions = actions_dev;
     a.actions_out = next_actions_dev;
-    a.rule = rule; a.coin_mode = coin_mode; a.seed = seed; a.step_index = step_index;
+    a.rule = rule; a.coin_mode = coin_mode; a.seed = seed; a.step_index = step_index; a.cr_factor = h->cr_factor;
     return launch_all(h, a, false, (cudaStream_t)stream);
 }
 
@@ -521,7 +528,7 @@ int jss_policy(jss_t *h, int rule, int coin_mode, uint64_t seed, uint64_t step_i
         return fail(h, JSS_ERR_INVALID, "jss_policy: bad arguments (rule %d, coin %d)", rule, coin_mode);
     JssLaunch a{};
     a.mode = JSS_MODE_POLICY;
-    a.rule = rule; a.coin_mode = coin_mode; a.seed = seed; a.step_index = step_index;
+    a.rule = rule; a.coin_mode = coin_mode; a.seed = seed; a.step_index = step_index; a.cr_factor = h->cr_factor;
     a.actions_out = actions_dev;
     return launch_all(h, a, rule_wants_rem(rule), (cudaStream_t)stream);
 }
@@ -533,7 +540,7 @@ int jss_rollout(jss_t *h, int rule, uint64_t seed, uint64_t step_index, int n_st
         return fail(h, JSS_ERR_INVALID, "jss_rollout: bad arguments (rule %d, n_steps %d)", rule, n_steps);
     JssLaunch a{};
     a.mode = JSS_MODE_ROLLOUT;
-    a.rule = rule; a.coin_mode = JSS_COIN_DEVICE; a.seed = seed; a.step_index = step_index;
+    a.rule = rule; a.coin_mode = JSS_COIN_DEVICE; a.seed = seed; a.step_index = step_index; a.cr_factor = h->cr_factor;
     a.n_steps = n_steps; a.write_obs = write_obs;
     return launch_all(h, a, rule_wants_rem(rule), (cudaStream_t)stream);
 }

@@ -627,7 +627,7 @@ JSS_DEV bool env_step(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, in
 // ---- policies (JSSEnv/dispatching.py; README.md:58-60) ---------------------------------
 template <int KJ, bool RANDOM_ONLY = false>
 JSS_DEV int env_select_action(const InstView &iv, const EnvRegs<KJ> &s, int lane, int rule, int coin_mode,
-                              uint32_t h) {
+                              uint32_t h, double cr_factor) {
     constexpr uint32_t LM = jss_legal_mask<KJ>();
     const uint32_t mine = (uint32_t)__popc(s.lb & LM);
     // inclusive prefix count of legal jobs over the lanes (ascending job index order)
@@ -666,7 +666,7 @@ JSS_DEV int env_select_action(const InstView &iv, const EnvRegs<KJ> &s, int lane
         for (int i = 0; i < KJ; i++) {
             const int j = KJ * lane + i;
             if (s.lb & (1u << i)) {
-                const double due = (double)iv.len[j] * 1.5;                          // :357-360
+                const double due = (double)iv.len[j] * cr_factor;                    // :357-360
                 const int remaining = iv.rem[j * (iv.si->M + 1) + s.todo[i]];            // :387-388
                 const double ratio = remaining > 0 ? (due - (double)s.t) / (double)remaining : 1.0 / 0.0;
                 if (ratio < key) { key = ratio; kj = j; }                            // strict <, first index wins
@@ -832,7 +832,7 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
     if (mode == JSS_MODE_EXPORT) { env_export<KJ>(p, iv, s, env, lane); return; }
     if (mode == JSS_MODE_POLICY) {
         const uint32_t h = jss_hash3(a.seed, genv, a.step_index);
-        const int act = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h);
+        const int act = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
         if (lane == 0) a.actions_out[env] = act;
         return;
     }
@@ -858,7 +858,7 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
     int raw = 0;
     for (int k = 0; k < a.n_steps; k++) {
         const uint32_t h = jss_hash3(a.seed, genv, a.step_index + (uint64_t)k);
-        const int act = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h);
+        const int act = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
         int r = 0;
         const bool changed = env_step<KJ>(p, iv, s, env, lane, act, r, hz);
         if (changed) {
@@ -1014,7 +1014,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
         const bool changed = env_step<KJ>(p, iv, s, env, lane, action, raw, reinterpret_cast<int *>(scratch));
         if (SAMPLE) {
             const uint32_t h = jss_hash3(a.seed, p.env_id_base + (uint64_t)env, a.step_index);
-            const int nxt = env_select_action<KJ, SAMPLE == 1>(iv, s, lane, a.rule, a.coin_mode, h);
+            const int nxt = env_select_action<KJ, SAMPLE == 1>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
             if (lane == 0) a.actions_out[env] = nxt;
         }
         if (changed) {

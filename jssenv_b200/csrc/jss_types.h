@@ -81,6 +81,7 @@ struct JssLaunch {           // per-launch arguments
     int32_t mode;            // JSS_MODE_*
     int32_t rule, coin_mode, n_steps, write_obs;
     uint64_t seed, step_index;
+    double cr_factor;        // CriticalRatio due_date_factor (dispatching.py:337-349); reference default 1.5
     const int32_t *actions;  // step
     int32_t *actions_out;    // policy
     const uint8_t *env_mask; // reset / import

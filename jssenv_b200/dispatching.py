@@ -21,7 +21,11 @@ class DispatchingRule:
         self.name = name
         self.description = description
 
+    def _prepare(self, env) -> None:
+        """Rule parameters that live in the native handle (only CR has one)."""
+
     def __call__(self, env) -> int:
+        self._prepare(env)
         action, noop_legal = env.rule_action(self.name)
         if action == env.jobs:                 # only the no-op is legal (e.g. dispatching.py:96-97): no draw
             return action
@@ -49,6 +53,7 @@ class DispatchingRule:
     def run_batch(self, vec_env, max_steps: Optional[int] = None, chunk: int = 256):
         """Whole-batch episodes on device: returns (raw returns int32[N], makespans int32[N]).
         Envs are reset first; each env stops at its own `done` (frozen afterwards)."""
+        self._prepare(vec_env)
         vec_env.reset()
         if max_steps is None:
             # a transition either allocates an op (J*M of them) or advances time (at most one
@@ -85,13 +90,14 @@ LeastOperationsRemaining = _mk("LeastOperationsRemaining", "LOR",
 
 
 class CriticalRatio(DispatchingRule):
-    """dispatching.py:327-408; the device kernel uses due_date_factor = 1.5 (the reference default)."""
+    """dispatching.py:327-408; ``due_date_factor`` (:337-349) is a launch parameter of the device rule."""
 
     def __init__(self, due_date_factor: float = 1.5):
         super().__init__("CR", "Critical Ratio: Schedule based on the ratio of time to due date versus remaining work")
-        if due_date_factor != 1.5:
-            raise ValueError("the device CR rule implements the reference default due_date_factor=1.5 only")
-        self.due_date_factor = due_date_factor
+        self.due_date_factor = float(due_date_factor)
+
+    def _prepare(self, env) -> None:
+        env.set_cr_due_date_factor(self.due_date_factor)
 
 
 DISPATCHING_RULES = {

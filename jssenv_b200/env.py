@@ -141,7 +141,9 @@ class JssEnv(_gym.Env if _gym is not None else object):
             # the reference raises IndexError here (jss_env.py:444 / :517) or silently corrupts
             # its counters (illegal job action); the device env sets the sticky error bit
             self._raise_for_error(f"illegal action {a} for the current state")
-        reward = float(self._vec.reward[0])
+        # float64 quotient like the reference's _reward_scaler (jss_env.py:483-493); the device record holds the
+        # exact integer numerator next to its fp32 quotient
+        reward = float(int(self._vec.reward_raw[0])) / float(self.max_time_op)
         done = bool(self._vec.done[0])
         if done:                                               # jss_env.py:649-652
             self.last_time_step = self.current_time_step
@@ -155,6 +157,9 @@ class JssEnv(_gym.Env if _gym is not None else object):
         if self._flags & N.FLAG_ERROR:
             self._raise_for_error("pop from empty list")      # what the reference raises (jss_env.py:517)
         return -int(self._vec.reward_raw[0])
+
+    def set_cr_due_date_factor(self, factor: float):
+        self._vec.set_cr_due_date_factor(factor)
 
     def rule_action(self, rule: str):
         """(action, noop_legal) chosen on device by a dispatching rule, without the 10 % coin."""

@@ -174,6 +174,10 @@ class JssVecEnv:
         N.check(self._h, rc, "jss_policy")
         return out
 
+    def set_cr_due_date_factor(self, factor: float):
+        """CriticalRatio(due_date_factor) of the reference (dispatching.py:337-349) for later CR launches."""
+        N.check(self._h, self._L.jss_set_cr_due_date_factor(self._h, float(factor)), "jss_set_cr_due_date_factor")
+
     def rollout(self, rule: Union[str, int], n_steps: int, write_obs: bool = True):
         """n_steps x (policy -> step) fused on device (DispatchingRule.run_episode, dispatching.py:55-75)."""
         r = N.RULES[rule.upper()] if isinstance(rule, str) else int(rule)

@@ -13,6 +13,7 @@ Outputs
         plus the integer state arrays after every step
   tests/golden/known_answers.json       steps / makespan / sum(reward) of whole episodes under the
                                         deterministic "lowest/highest legal index" policies
+  tests/golden/cr_factor_makespans.json CriticalRatio(due_date_factor=1.0 / 2.25 / 4.0), np.random.seed(0)
   tests/golden/rule_makespans.json      makespans of every dispatching rule with
                                         np.random.seed(0) before run_episode
 """
@@ -168,6 +169,17 @@ def main():
             rules[inst][name] = {"makespan": int(makespan), "total_reward": float(total_reward)}
         print(inst, {k: v["makespan"] for k, v in rules[inst].items()})
     json.dump(rules, open(os.path.join(GOLD, "rule_makespans.json"), "w"), indent=1)
+
+    # CriticalRatio with non-default due_date_factor (dispatching.py:337-349)
+    crf = {}
+    for inst in ("ta01", "ta41", "ta80"):
+        crf[inst] = {}
+        for f in (1.0, 2.25, 4.0):
+            env = JssEnv({"instance_path": reference_instance_path(inst)})
+            np.random.seed(0)
+            total_reward, makespan = dispatching.CriticalRatio(due_date_factor=f).run_episode(env)
+            crf[inst][str(f)] = {"makespan": int(makespan), "total_reward": float(total_reward)}
+    json.dump(crf, open(os.path.join(GOLD, "cr_factor_makespans.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -46,6 +46,7 @@
 
 typedef struct jsso {
     int jobs, machines;
+    double cr_due_date_factor; /* CriticalRatio.__init__(due_date_factor=1.5), dispatching.py:337-349 */
     int64_t *inst_machine;   /* instance_matrix[j][op][0]  [J*M] */
     int64_t *inst_time;      /* instance_matrix[j][op][1]  [J*M] */
     int64_t *jobs_length;    /* [J] */
@@ -88,6 +89,7 @@ jsso *jsso_create(int jobs, int machines, const int32_t *machine, const int32_t 
     size_t J = (size_t)jobs, M = (size_t)machines;
     o->jobs = jobs;
     o->machines = machines;
+    o->cr_due_date_factor = 1.5;
     o->inst_machine = (int64_t *)zalloc(J * M * 8);
     o->inst_time = (int64_t *)zalloc(J * M * 8);
     o->jobs_length = (int64_t *)zalloc(J * 8);
@@ -460,7 +462,7 @@ int jsso_rule_action(jsso *o, int rule, double u, int *consumed) {
         case 6: {
             int64_t total_time = 0;
             for (int op = 0; op < M; op++) total_time += IT(o, job, op);      /* :357 */
-            double due_date = (double)total_time * 1.5;                        /* :360 */
+            double due_date = (double)total_time * o->cr_due_date_factor;      /* :360 */
             for (int64_t op = todo; op < M; op++) remaining += IT(o, job, op); /* :387-388 */
             double time_remaining = due_date - (double)o->current_time_step;   /* :391 */
             if (remaining > 0) key = time_remaining / (double)remaining;       /* :396 */
@@ -486,6 +488,7 @@ int jsso_rule_action(jsso *o, int rule, double u, int *consumed) {
 }
 
 /* ---- accessors for the ctypes wrapper --------------------------------- */
+void jsso_set_cr_due_date_factor(jsso *o, double f) { o->cr_due_date_factor = f; }
 int jsso_jobs(const jsso *o) { return o->jobs; }
 int jsso_machines(const jsso *o) { return o->machines; }
 int64_t jsso_scalar(const jsso *o, int which) {

@@ -38,6 +38,8 @@ def lib():
                                 ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int)]
         L.jsso_increase_time_step.argtypes = [vp, ctypes.POINTER(ctypes.c_int64)]
         L.jsso_rule_action.argtypes = [vp, ctypes.c_int, ctypes.c_double, ctypes.POINTER(ctypes.c_int)]
+        L.jsso_set_cr_due_date_factor.argtypes = [vp, ctypes.c_double]
+        L.jsso_set_cr_due_date_factor.restype = None
         L.jsso_scalar.restype = ctypes.c_int64
         L.jsso_scalar.argtypes = [vp, ctypes.c_int]
         L.jsso_array.restype = vp
@@ -155,6 +157,10 @@ class OracleEnv:
         if rc != 0:
             raise OracleError("pop from empty list")
         return int(hole.value)
+
+    def set_cr_due_date_factor(self, factor: float):
+        """CriticalRatio(due_date_factor=...) of the reference (dispatching.py:337-349); default 1.5."""
+        self._L.jsso_set_cr_due_date_factor(self._h, float(factor))
 
     def rule_action(self, rule: str, u: float):
         """Returns (action, consumed): `consumed` says whether the reference would

@@ -192,6 +192,14 @@ def check_rules_seeded(inst):
         total, makespan = rule.run_episode(env)
         assert makespan == gold[name]["makespan"], (inst, name)
         assert abs(total - gold[name]["total_reward"]) <= 1e-3, (inst, name)
+    if inst in load_json("cr_factor_makespans.json"):      # CriticalRatio(due_date_factor) as a launch parameter
+        from jssenv_b200.dispatching import CriticalRatio
+        for f, exp in load_json("cr_factor_makespans.json")[inst].items():
+            np.random.seed(0)
+            total, makespan = CriticalRatio(due_date_factor=float(f)).run_episode(env)
+            assert makespan == exp["makespan"] and abs(total - exp["total_reward"]) <= 1e-3, (inst, f)
+        np.random.seed(0)
+        assert DISPATCHING_RULES["CR"].run_episode(env)[1] == gold["CR"]["makespan"]   # default factor restored
     try:
         get_rule("NOPE")
         raise AssertionError("get_rule must raise ValueError")   # tests/test_dispatching.py:39-47
@@ -599,3 +607,39 @@ def check_tiny_uniform_batches(make_env, seed=50):
                          "episode_count", "last_makespan", "last_return"):
                 assert np.array_equal(_np(getattr(a_env, name)), _np(getattr(b_env, name))), (J, M, rule, name)
             assert a_env.stats() == b_env.stats() and a_env.stats()["envs_error"] == 0
+
+
+def check_shard_invariance(make_env, n_total=24, n_steps=350, seed=77):
+    """results must not depend on how the global batch is sharded.
+    One env of N_total envs == the shards [0, N/2) and [N/2, N) created with env_id_base = 0 and N/2 (and an
+    uneven 3-way split), transition for transition, with the on-device policies (RNG keyed by GLOBAL env id)."""
+    names = ["ta01", "ta31", "ta51", "ta80"]
+    e2i = np.arange(n_total) % len(names)
+    for rule in ("RANDOM", "FIFO"):
+        whole = make_env(n_total, {"instance_paths": names, "env_to_instance": e2i}, seed=seed, auto_reset=True)
+        cuts = [0, n_total // 2, n_total]
+        cuts3 = [0, 5, 5 + 9, n_total]
+        for cut in (cuts, cuts3):
+            shards = [make_env(hi - lo, {"instance_paths": names, "env_to_instance": e2i[lo:hi]}, seed=seed,
+                               auto_reset=True, env_id_base=lo) for lo, hi in zip(cut[:-1], cut[1:])]
+            whole.reset(); whole._step_index = 0
+            for s in shards:
+                s.reset()
+            for k in range(n_steps):
+                aw = whole.policy(rule)
+                for s, lo, hi in zip(shards, cut[:-1], cut[1:]):
+                    a_s = s.policy(rule)
+                    assert np.array_equal(_np(a_s), _np(aw)[lo:hi]), (rule, k, lo)
+                    s.step(a_s)
+                whole.step(aw)
+                for s, lo, hi in zip(shards, cut[:-1], cut[1:]):
+                    for name in ("action_mask", "real_obs", "reward", "reward_raw", "done", "current_time_step",
+                                 "episode_count", "last_makespan"):
+                        assert np.array_equal(_np(getattr(s, name)), _np(getattr(whole, name))[lo:hi]), (rule, k, name)
+            # the gathered per-shard statistics equal the statistics of the unsharded batch
+            from jssenv_b200.distributed import combine_stats, STATS_KEYS
+            comb = combine_stats([[s.stats()[key] for key in STATS_KEYS] for s in shards])
+            assert comb == {**whole.stats(), "min_makespan": comb["min_makespan"]} or comb == whole.stats()
+            for s in shards:
+                s.close()
+        whole.close()

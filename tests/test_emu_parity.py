@@ -140,3 +140,7 @@ def test_emu_dispatching_api():
 
 def test_emu_tiny_uniform_batches():
     pc.check_tiny_uniform_batches(make_env)
+
+
+def test_emu_shard_invariance():
+    pc.check_shard_invariance(make_env, n_steps=150)

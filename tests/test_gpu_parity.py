@@ -272,3 +272,7 @@ def test_gpu_soak_auto_reset_full_size():
 
 def test_gpu_tiny_uniform_batches():
     pc.check_tiny_uniform_batches(make_env)
+
+
+def test_gpu_shard_invariance():
+    pc.check_shard_invariance(make_env, n_total=48, n_steps=2400)
