@@ -1,14 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- env steps/sec of the batched job-shop environment on B200.
 
-One "step" = one pass of the hot path over the whole batch: the device masked-uniform
-policy kernel picks an action per env, the fused step kernel applies it (time
-advance, legal-action heuristics, observation, mask, reward, done all written to
-HBM).  Workload = BASELINE.json configs[2]: N = 65 536 concurrent ta80 (100x20)
-envs per GPU, auto-reset, weak scaling across GPUs (no per-step communication; one
-NCCL all-gather of the per-shard episode statistics at the end).
+One "step" = one pass of the hot path over the whole batch: ONE fused launch applies every env's
+action (time advance, legal-action heuristics, observation, mask, reward, done all written to HBM)
+and samples the next action with the device masked-uniform policy.  Headline workload =
+BASELINE.json configs[2]: N = 65 536 concurrent ta80 (100x20) envs per GPU, auto-reset, weak scaling
+across GPUs (no per-step communication; one NCCL all-gather of the per-shard episode statistics).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+The same JSON line carries, under "configs", the other BASELINE.json configurations measured in the
+same run (cfg2 ta01 N=4096, cfg4 ta80 N=262144 in total over the ranks, cfg5 mixed ta01..ta80 with
+the on-device FIFO / MWR rules), each with its algorithmic bytes and HBM-roofline fraction, and under
+"cpu_baseline" the reference's CPU path timed on this box's host cores: the C oracle port AND the
+unmodified Python reference (oracle/_ref, installed by oracle/install_ref.py).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--configs all|none]
 """
 import argparse
 import json
@@ -26,6 +31,7 @@ if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
 
 METRIC = "env steps/sec (N=65536 ta80)"
 UNIT = "env_steps/s"
+TA80_EPISODE = 2236          # masked-random episode length on ta80: pre-roll period
 
 
 def b_alg(J, M):
@@ -64,6 +70,16 @@ def usable_cpus():
         except Exception:
             pass
     return n
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
 
 class ClockSampler:
@@ -108,11 +124,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_leg(instance, budget_s, threads=None):
-    """The reference's CPU path restated in C (oracle/jss_oracle.c, kind "port": the reference is
-    pure Python and cannot travel to the GPU box), masked-uniform policy, auto-reset, one env per
-    host thread, all host threads.  Returns (steps/s, threads, sample description)."""
-    import numpy as np
+# ------------------------------------------------------------------------------------------ CPU legs
+def cpu_port_leg(instance, budget_s, threads=None):
+    """The reference's CPU path restated in C (oracle/jss_oracle.c, kind "port"), masked-uniform policy,
+    auto-reset, one env per host thread, all usable host threads.  Returns (steps/s, threads, sample)."""
     from jssenv_b200.instances import load_instance
     from oracle.jss_oracle import OracleEnv
     P = threads or usable_cpus()
@@ -136,9 +151,69 @@ def cpu_reference_leg(instance, budget_s, threads=None):
                            f"{instance} steps (masked-random, auto-reset): {steps} steps")
 
 
+def py_ref_worker(instance, seconds, seed):
+    """ONE worker process of the Python-reference leg: the UNMODIFIED reference JssEnv (oracle/_ref or
+    /root/reference through oracle/ref_shim.py), masked-uniform policy (np.flatnonzero + Generator.integers,
+    BASELINE.md section 3), auto-reset; 1 s warm-up, then `seconds` of wall time.  Prints one JSON line."""
+    import numpy as np
+    from oracle.ref_shim import load_reference, reference_instance_path
+    JssEnv, _ = load_reference()
+    env = JssEnv({"instance_path": reference_instance_path(instance)})
+    rng = np.random.default_rng(seed)
+    obs = env.reset()
+    steps = resets = 0
+    t_step = 0.0
+    clock = time.perf_counter
+    t_warm = clock() + 1.0
+    t_end = None
+    while True:
+        now = clock()
+        if t_end is None:
+            if now >= t_warm:
+                t_end, t_begin, steps, resets, t_step = now + seconds, now, 0, 0, 0.0
+        elif now >= t_end:
+            break
+        legal = np.flatnonzero(obs["action_mask"])
+        a = int(legal[rng.integers(len(legal))])
+        t0 = clock()
+        obs, _, done, _, _ = env.step(a)
+        t_step += clock() - t0
+        steps += 1
+        if done:
+            obs = env.reset()
+            resets += 1
+    print(json.dumps({"steps": steps, "resets": resets, "elapsed": clock() - t_begin, "step_only_s": t_step}))
+
+
+def python_reference_leg(instance, seconds, procs=None):
+    """P worker PROCESSES (the reference is single-threaded Python; the GIL rules out threads), each owning one
+    unmodified reference env.  Returns a dict, or {"unavailable": why}."""
+    from oracle.ref_shim import reference_available, REFERENCE_ROOT
+    if not reference_available():
+        return {"unavailable": "unmodified reference not installed (oracle/install_ref.py needs /root/reference)"}
+    P = procs or usable_cpus()
+    cmd = [sys.executable, os.path.abspath(__file__), "--py-ref-worker", instance, str(seconds)]
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen(cmd + [str(i)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for i in range(P)]
+    outs = []
+    for pr in ps:
+        so, se = pr.communicate(timeout=seconds * 6 + 120)
+        if pr.returncode != 0:
+            return {"unavailable": "reference worker failed: " + se.strip().splitlines()[-1][:200]}
+        outs.append(json.loads(so.strip().splitlines()[-1]))
+    wall = time.perf_counter() - t0
+    total = sum(o["steps"] / o["elapsed"] for o in outs)
+    step_only = sum(o["step_only_s"] for o in outs) / max(1, sum(o["steps"] for o in outs))
+    return {"value": total, "unit": UNIT, "cores": P, "per_core": total / P, "step_only_us": step_only * 1e6,
+            "kind": "reference", "cpu": cpu_model(), "source": os.path.relpath(REFERENCE_ROOT, ROOT) if REFERENCE_ROOT.startswith(ROOT) else REFERENCE_ROOT,
+            "sample": f"{P} worker processes x {seconds:.0f} s (after 1 s warm-up) of the UNMODIFIED Python reference JssEnv.step() on "
+                      f"{instance}, masked-random policy, resets included: {sum(o['steps'] for o in outs)} steps, wall {wall:.1f} s"}
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (C oracle port, the Python reference cannot travel to the
-    GPU box) on all usable host threads; each "step" is one bounded wall-time window of the workload."""
+    """--impl reference: the reference's CPU path on all usable host threads.  value = the C oracle port (the
+    stronger baseline: ~75x faster per core than the Python original); the unmodified Python reference timed on the
+    same box is reported beside it.  Each "step" is one bounded wall-time window of the workload."""
     if rank != 0:
         return
     J, M = 100, 20
@@ -146,21 +221,74 @@ def run_reference(args, rank, world):
     warm = 1 if args.warmup > 0 else 0
     vals, sample, P = [], "", 1
     for k in range(warm + windows):
-        v, P, sample = cpu_reference_leg("ta80", 2.0 if k < warm else args.cpu_seconds)
+        v, P, sample = cpu_port_leg("ta80", 2.0 if k < warm else args.cpu_seconds)
         if k >= warm:
             vals.append(v)
     value = sum(vals) / len(vals)
+    pyref = python_reference_leg("ta80", args.cpu_seconds)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": "ta80 (100x20) masked-random, auto-reset, CPU oracle port of the reference step()",
                    "envs": P, "bytes_per_env_step": b_alg(J, M), "timed_windows": windows,
-                   "window_seconds": args.cpu_seconds,
-                   "python_reference_steps_per_s_per_core": 4378},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": P, "kind": "port", "sample": sample},
+                   "window_seconds": args.cpu_seconds},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": P, "kind": "port", "sample": sample, "cpu": cpu_model(),
+                         "python_reference": pyref},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ------------------------------------------------------------------------------------------ GPU legs
+def preroll(env, rule, period, torch):
+    """Stagger the envs' episode phases deterministically before timing: env i executes (i * 7919) mod `period`
+    transitions (auto-reset keeps short episodes cycling), the others are skipped (JSS_ACTION_SKIP), so that a
+    short timed window samples the stationary mix of episode phases instead of `period` envs in lock-step."""
+    n = env.num_envs
+    ids = torch.arange(n, device=env.device, dtype=torch.int64) + int(env.env_id_base)
+    quota = ((ids * 7919) % period).to(torch.int32)
+    skip = torch.full((n,), -1, dtype=torch.int32, device=env.device)
+    for k in range(period):
+        a = env.policy(rule)
+        env.step(torch.where(quota > k, a, skip))
+    return env.policy(rule).clone()
+
+
+def time_fused_steps(env, rule, acts, warm, steps, torch, dist=None, world=1):
+    """`steps` fused launches (apply actions + choose the next ones) between CUDA events on the launching stream."""
+    for _ in range(warm):
+        *_, acts = env.step_sample(acts, rule)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = env.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        *_, acts = env.step_sample(acts, rule)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = env.launch_count - l0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, launches, acts
+
+
+def config_entry(workload, n_total, ms, steps, mean_balg, peak, launches, world=1, extra=None):
+    per_step = ms / steps
+    d = {"workload": workload, "envs_total": n_total, "steps": steps, "ms_per_step": per_step,
+         "env_steps_per_s": n_total * steps / (ms * 1e-3), "bytes_per_env_step": mean_balg,
+         "achieved_GBps_per_gpu": mean_balg * (n_total / world) / (per_step * 1e-3) / 1e9,
+         "launches_per_step": launches / steps}
+    d["frac_of_hbm_peak"] = d["achieved_GBps_per_gpu"] / peak
+    if extra:
+        d.update(extra)
+    return d
 
 
 def main():
@@ -173,15 +301,29 @@ def main():
     ap.add_argument("--instance", default="ta80")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--configs", default="all", choices=["all", "none"], help="also measure cfg2 / cfg4 / cfg5")
+    ap.add_argument("--config-steps", type=int, default=0, help="timed steps of the secondary configs (default max(K, 300))")
+    ap.add_argument("--no-preroll", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--py-ref-worker", nargs=3, metavar=("INSTANCE", "SECONDS", "SEED"), help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.py_ref_worker:
+        py_ref_worker(args.py_ref_worker[0], float(args.py_ref_worker[1]), int(args.py_ref_worker[2]))
+        return
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+
+    # CPU baselines first (N = 1 only, before any CUDA context exists in this process)
+    cpu_baseline = None
+    if not args.no_cpu and world == 1:
+        v, P, sample = cpu_port_leg(args.instance, args.cpu_seconds)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": P, "kind": "port", "sample": sample, "cpu": cpu_model(),
+                        "python_reference": python_reference_leg(args.instance, args.cpu_seconds)}
 
     import numpy as np
     import torch
@@ -201,40 +343,24 @@ def main():
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
+    peak, peak_src = load_peaks()
     N = args.envs
+    K, W = args.steps, max(3, args.warmup)
     env = JssVecEnv(N, {"instance_path": args.instance}, device=local_rank, auto_reset=True,
                     env_id_base=rank * N, seed=1234)
     J, M = env.jobs, env.machines
-    K, W = args.steps, max(3, args.warmup)
-
     env.reset()
-    acts = env.policy("RANDOM").clone()
-    for _ in range(W):
-        *_, acts = env.step_sample(acts, "RANDOM")
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    if args.no_preroll:
+        acts = env.policy("RANDOM").clone()
+    else:
+        acts = preroll(env, "RANDOM", TA80_EPISODE if J * M >= 2000 else int(1.13 * J * M), torch)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = env.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ev0.record()
-    for k in range(K):
-        *_, acts = env.step_sample(acts, "RANDOM")     # one launch: apply actions, sample the next ones
-    ev1.record()
-    torch.cuda.synchronize()
-    launches = env.launch_count - l0
-    elapsed_ms = ev0.elapsed_time(ev1)
+    elapsed_ms, launches, acts = time_fused_steps(env, "RANDOM", acts, W, K, torch, dist, world)
+    clocks = sampler.stop()
     # the timed region is K launches of ONE kernel (the fused step), bracketed by CUDA events on the
     # launching stream: its average launch duration is elapsed / K (launch gaps, if any, count against us)
     step_kernel_ms = elapsed_ms / K
-    clocks = sampler.stop()
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
     stats = all_gather_stats(env.stats())
     value = world * N * K / (elapsed_ms * 1e-3)
 
@@ -242,8 +368,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         # pipelined host-buffer API: begin(step k) -> wait mask k -> host policy -> begin(step k+1) while the
-        # 2.9 KB/env observation of step k is still crossing PCIe into its own pinned buffer -> consume obs k
-        env.reset()
+        # observation of step k is still crossing PCIe into its own pinned buffer -> consume obs k
         mask = np.ascontiguousarray(env.action_mask.cpu().numpy())
         env.host_step_begin(env.host_masked_random(mask, 0))
         checksum = 0.0
@@ -273,18 +398,66 @@ def main():
                "steps": args.e2e_steps,
                "note": "jss_host_step_begin / jss_host_wait (pinned host buffers): H2D actions, step kernel, D2H mask + "
                        "scalars + real_obs every step; host masked-random policy from the host mask; PCIe-bound"}
+    env.close()
+    del env
+
+    # ---- the other BASELINE.json configurations, same run, same timing method
+    configs = {}
+    if args.configs == "all":
+        KC = args.config_steps or max(K, 300)
+        if world == 1:
+            # cfg2: ta01 N = 4096, masked-random
+            e2 = JssVecEnv(4096, {"instance_path": "ta01"}, device=local_rank, auto_reset=True, seed=1)
+            e2.reset()
+            a2 = e2.policy("RANDOM").clone() if args.no_preroll else preroll(e2, "RANDOM", 253, torch)
+            ms, ln, a2 = time_fused_steps(e2, "RANDOM", a2, W, KC, torch)
+            configs["cfg2_ta01_N4096_random"] = config_entry(
+                "ta01 (15x15) N=4096, masked-random, one fused launch per step, obs/mask/reward/done written every step",
+                4096, ms, KC, b_alg(15, 15), peak, ln,
+                extra={"note": "5 MB per step: L2-resident and < 1 wave (4096 warps) -> launch/latency-bound by construction"})
+            e2.close()
+            del e2
+            # cfg5: mixed ta01..ta80 N = 65536, on-device FIFO / MWR (+ masked-random for comparison)
+            names = ["ta%02d" % (k + 1) for k in range(80)]
+            n5 = 65536
+            e5 = JssVecEnv(n5, {"instance_paths": names, "env_to_instance": np.arange(n5) % 80}, device=local_rank,
+                           auto_reset=True, seed=2)
+            balg5 = float(np.mean([b_alg(int(j), int(m)) for j, m in zip(e5.env_jobs, e5.env_machines)]))
+            for rule in ("FIFO", "MWR", "RANDOM"):
+                e5.reset()
+                a5 = e5.policy(rule).clone() if args.no_preroll else preroll(e5, rule, TA80_EPISODE, torch)
+                ms, ln, a5 = time_fused_steps(e5, rule, a5, W, KC, torch)
+                configs[f"cfg5_mixed_ta01-80_N65536_{rule}"] = config_entry(
+                    f"env i runs ta((i mod 80)+1), N=65536, on-device {rule} rule (10 % no-op coin from the counter RNG), "
+                    "fused step + rule per step, obs written every step", n5, ms, KC, balg5, peak, ln)
+            e5.close()
+            del e5
+        # cfg4 as stated: ta80 N = 262144 IN TOTAL, sharded over the ranks (8 x 32768 at --gpus 8)
+        n4 = 262144 // world
+        e4 = JssVecEnv(n4, {"instance_path": "ta80"}, device=local_rank, auto_reset=True, env_id_base=rank * n4, seed=4)
+        e4.reset()
+        a4 = e4.policy("RANDOM").clone() if args.no_preroll else preroll(e4, "RANDOM", TA80_EPISODE, torch)
+        ms, ln, a4 = time_fused_steps(e4, "RANDOM", a4, W, KC, torch, dist, world)
+        st4 = all_gather_stats(e4.stats())
+        configs["cfg4_ta80_N262144_total"] = config_entry(
+            f"ta80 N=262144 in total = {world} x {n4} (contiguous shards, no per-step communication, NCCL all-gather of the "
+            "per-shard statistics)", 262144, ms, KC, b_alg(100, 20), peak, ln, world=world,
+            extra={"scaling": "strong", "episodes_gathered": st4["episodes"]})
+        e4.close()
+        del e4
 
     if rank == 0:
-        peak, peak_src = load_peaks()
         balg = b_alg(J, M)
         achieved = balg * N / (step_kernel_ms * 1e-3) / 1e9
-        traffic = None                                   # dram__bytes_read+write per launch from the committed ncu capture
+        traffic, traffic_src = None, None               # dram__bytes_read+write per launch: OFFLINE data from the committed ncu capture
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             if tj["n_envs"] == N and tj["instance"] == args.instance:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                traffic_src = "offline: ncu --set full capture committed under profiles/ (" + tj.get("source", "traffic.json") + ")"
         except Exception:
             pass
+        kj = 1 if J <= 32 else (2 if J <= 64 else 4)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -292,19 +465,21 @@ def main():
             "config": {"workload": f"{args.instance} ({J}x{M}) N={N} per GPU, one fused launch per step (apply actions + masked-random "
                                    "sampling of the next ones), auto-reset", "envs_per_gpu": N, "parallelism": f"env-shard x{world}",
                        "l2": "per-step working set (state 140 MB + obs 190 MB at N=65536) exceeds the 126 MB L2",
+                       "preroll": "none" if args.no_preroll else "env i pre-stepped (i*7919 mod 2236) transitions: the timed window sees the stationary mix of episode phases",
                        "bytes_per_env_step": balg},
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": balg * N, "kernel": "jss_step_kernel<4, sample>", "kernel_ms": step_kernel_ms,
+                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": balg * N,
+                         "kernel": f"jss_step_kernel<KJ={kj}, fused sampler, uniform batch>", "kernel_ms": step_kernel_ms,
                          "peak_source": peak_src},
             "episode_stats": stats,
         }
         if e2e:
             out["e2e"] = e2e
-        if not args.no_cpu and world == 1:               # the CPU baseline is reported at N = 1 only
-            v, P, sample = cpu_reference_leg(args.instance, args.cpu_seconds)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": P, "kind": "port", "sample": sample,
-                                   "python_reference_steps_per_s_per_core": 4378}
+        if configs:
+            out["configs"] = configs
+        if cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

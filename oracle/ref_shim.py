@@ -3,8 +3,10 @@
 TEST INFRASTRUCTURE ONLY.  Used by ``oracle/gen_golden.py`` and
 ``tools/pack_instances.py`` to (a) validate the C restatement in
 ``oracle/jss_oracle.c`` and (b) generate the committed fixtures under
-``tests/golden/``.  ``/root/reference`` does not exist on the GPU box, so nothing
-in ``tests/ -m gpu``, ``bench.py`` or ``__graft_entry__.smoke()`` imports this.
+``tests/golden/``.  ``/root/reference`` does not exist on the GPU box; there the loader falls back to
+``oracle/_ref`` (the unmodified package installed by ``oracle/install_ref.py``, git-ignored,
+shipped with the snapshot), which is what ``bench.py``'s CPU legs time as the reference's own
+NumPy ``step()``.  Never imported by the product package.
 
 The reference needs ``gymnasium`` and ``plotly`` only for ``gym.Env`` /
 ``gym.spaces`` (jss_env.py:8,14,97,112-119) and for ``render`` (jss_env.py:10-11,
@@ -15,11 +17,23 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("JSS_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_INSTALLED = os.path.join(_HERE, "_ref")          # pip --target install made by oracle/install_ref.py (travels to the GPU box)
+
+
+def _pick_root():
+    env = os.environ.get("JSS_REFERENCE_ROOT")
+    for cand in (env, "/root/reference", _INSTALLED):
+        if cand and os.path.isfile(os.path.join(cand, "JSSEnv", "envs", "jss_env.py")):
+            return cand
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "JSSEnv"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "JSSEnv", "envs", "jss_env.py"))
 
 
 def _install_stubs():
