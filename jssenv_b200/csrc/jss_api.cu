@@ -8,6 +8,23 @@
 #include <cuda_runtime.h>
 #define JSS_SMEM_DECL(name) extern __shared__ uint4 name[]
 #define JSS_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+// launch with programmatic stream serialization (PDL): the kernel may start its prologue while the preceding
+// kernel in the stream drains; it calls griddepcontrol.wait before touching anything mutable
+template <typename... KArgs, typename... Args>
+static cudaError_t jss_launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#define JSS_LAUNCH_PDL(kern, grid, block, smem, stream, ...) jss_launch_pdl(kern, grid, block, smem, stream, __VA_ARGS__)
+#endif
+#ifdef JSS_EMU
+#define JSS_LAUNCH_PDL(kern, grid, block, smem, stream, ...) (JSS_LAUNCH(kern, grid, block, smem, stream, __VA_ARGS__), cudaSuccess)
 #endif
 
 #include <algorithm>
@@ -56,7 +73,9 @@ struct jss_handle {
     JssParams p{};
     JssSmemLayout sl_norem{}, sl_rem{};
     int class_tile_begin[3] = {0, 0, 0}, class_tile_end[3] = {0, 0, 0};  // KJ = 1, 2, 4
-    int step_grid[12] = {0};
+    int step_grid[16] = {0};                        // resident-CTA grids of the step kernel variants (filled lazily)
+    int ticket_parity = 0;                          // mixed-batch step kernel: which ticket counter the next launch draws from
+    bool use_pdl = true;
     std::vector<int32_t> env_inst;
 
     // host-buffer stepping
@@ -107,27 +126,27 @@ size_t smem_bytes(const JssSmemLayout &sl) {
     return sizeof(SmInst) + (size_t)sl.ops_elems * 2 + (size_t)sl.len_elems * 4 + (size_t)sl.rem_elems * 2 +
            (size_t)JSS_WARPS_PER_CTA * sl.scratch_words * 4;
 }
-template <int KJ, int SAMPLE, bool UNI>
-int launch_step_variant(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStream_t st) {
-    JssLaunch a = a_in;
-    if (UNI) {
-        const JssInstDesc &d = h->descs[h->p.uniform_inst];
-        SmInst &u = a.uni;
-        u.J = d.J; u.M = d.M; u.max_time_op = d.max_time_op; u.max_time_jobs = d.max_time_jobs; u.sum_op = d.sum_op;
-        u.f_mto = (float)d.max_time_op; u.f_mtj = (float)d.max_time_jobs; u.f_sop = (float)d.sum_op; u.f_M = (float)d.M;
-        u.r_mto = d.r_mto; u.r_mtj = d.r_mtj; u.r_sop = d.r_sop; u.r_M = d.r_M;
-    }
-    const int n_tiles = a.tile_end - a.tile_begin;
+void fill_uni(const JssInstDesc &d, SmInst &u) {
+    u.J = d.J; u.M = d.M; u.max_time_op = d.max_time_op; u.max_time_jobs = d.max_time_jobs; u.sum_op = d.sum_op;
+    u.f_mto = (float)d.max_time_op; u.f_mtj = (float)d.max_time_jobs; u.f_sop = (float)d.sum_op; u.f_M = (float)d.M;
+    u.r_mto = d.r_mto; u.r_mtj = d.r_mtj; u.r_sop = d.r_sop; u.r_M = d.r_M;
+    u.Jcap = round_up(d.J, 4); u.Mcap = round_up(d.M, 4); u.block_words = 5 * u.Jcap + u.Mcap + 12;
+}
+
+JssSmemLayout step_layout(jss_t *h, bool want_rem) {
     JssSmemLayout sl = want_rem ? h->sl_rem : h->sl_norem;
     sl.statein_words = h->p.block_words;
     sl.off_len = (int32_t)sizeof(SmInst) + sl.ops_elems * 2;
     sl.off_rem = sl.off_len + sl.len_elems * 4;
-    sl.off_warp0 = sl.off_rem + sl.rem_elems * 2;
+    sl.off_warp0 = sl.off_rem + sl.rem_elems * 2 + 16;       // 16 spare bytes: the mixed kernel's chunk ticket
     sl.off_scratch = 16 + sl.statein_words * 4;
     sl.warp_stride = sl.off_scratch + sl.scratch_words * 4 + sl.statein_words * 4;   // + state-out staging
-    const size_t smem = (size_t)sl.off_warp0 + (size_t)JSS_WARPS_PER_CTA * sl.warp_stride;
-    auto kern = jss_step_kernel<KJ, SAMPLE, UNI>;
-    int &grid = h->step_grid[(KJ == 1 ? 0 : (KJ == 2 ? 1 : 2)) * 4 + SAMPLE + (want_rem ? 1 : 0)];
+    return sl;
+}
+
+template <typename Kern>
+int step_grid_for(jss_t *h, Kern kern, int slot, size_t smem) {
+    int &grid = h->step_grid[slot];
     if (grid == 0) {                                     // once per handle: opt-in smem + occupancy
         if (smem > 48 * 1024)
             JSS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -136,23 +155,69 @@ int launch_step_variant(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStre
         if (per_sm < 1) return fail(h, JSS_ERR_CUDA, "step kernel does not fit on an SM (smem %zu B)", smem);
         grid = h->sm_count * per_sm;
     }
-    JSS_LAUNCH(kern, std::min(n_tiles, grid), JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl);
+    return JSS_OK;
+}
+
+// uniform batch: one instance, static strided tiles
+template <int KJ, int SAMPLE>
+int launch_step_uniform(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStream_t st) {
+    JssLaunch a = a_in;
+    fill_uni(h->descs[h->p.uniform_inst], a.uni);
+    a.tile_begin = 0;
+    a.tile_end = (h->n_envs + JSS_WARPS_PER_CTA - 1) / JSS_WARPS_PER_CTA;
+    const JssSmemLayout sl = step_layout(h, want_rem);
+    const size_t smem = (size_t)sl.off_warp0 + (size_t)JSS_WARPS_PER_CTA * sl.warp_stride;
+    auto kern = jss_step_kernel<KJ, SAMPLE>;
+    const int slot = (KJ == 1 ? 0 : (KJ == 2 ? 1 : 2)) * 4 + SAMPLE + (want_rem ? 1 : 0);
+    int rc = step_grid_for(h, kern, slot, smem);
+    if (rc) return rc;
+    const int grid = std::min(a.tile_end, h->step_grid[slot]);
+    if (h->use_pdl) JSS_CUDA(h, JSS_LAUNCH_PDL(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl));
+    else JSS_LAUNCH(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl);
     JSS_CUDA(h, cudaGetLastError());
     h->launches += 1;
     return JSS_OK;
 }
 
-template <int KJ>
+// mixed batch: ONE launch over all lane classes, chunks handed out by ticket
+template <int SAMPLE>
+int launch_step_mixed(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStream_t st) {
+    JssLaunch a = a_in;
+    a.ticket_parity = h->ticket_parity;
+    const JssSmemLayout sl = step_layout(h, want_rem);
+    const size_t smem = (size_t)sl.off_warp0 + (size_t)JSS_WARPS_PER_CTA * sl.warp_stride;
+    auto kern = jss_step_mixed_kernel<SAMPLE>;
+    const int slot = 12 + SAMPLE + (want_rem ? 1 : 0);
+    int rc = step_grid_for(h, kern, slot, smem);
+    if (rc) return rc;
+    const int grid = std::max(1, std::min(h->p.n_chunks, h->step_grid[slot]));
+    if (h->use_pdl) JSS_CUDA(h, JSS_LAUNCH_PDL(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl));
+    else JSS_LAUNCH(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl);
+    JSS_CUDA(h, cudaGetLastError());
+    h->ticket_parity ^= 1;
+    h->launches += 1;
+    return JSS_OK;
+}
+
 int launch_step(jss_t *h, const JssLaunch &a, cudaStream_t st) {
     const bool rem = a.rule == JSS_RULE_MWR || a.rule == JSS_RULE_LWR || a.rule == JSS_RULE_CR;
-    if (h->p.uniform_inst >= 0) {
-        if (a.actions_out == nullptr) return launch_step_variant<KJ, 0, true>(h, a, false, st);
-        if (a.rule == JSS_RULE_RANDOM) return launch_step_variant<KJ, 1, true>(h, a, false, st);
-        return launch_step_variant<KJ, 2, true>(h, a, rem, st);
+    const int sample = a.actions_out == nullptr ? 0 : (a.rule == JSS_RULE_RANDOM ? 1 : 2);
+    if (h->p.uniform_inst < 0) {
+        if (sample == 0) return launch_step_mixed<0>(h, a, false, st);
+        if (sample == 1) return launch_step_mixed<1>(h, a, false, st);
+        return launch_step_mixed<2>(h, a, rem, st);
     }
-    if (a.actions_out == nullptr) return launch_step_variant<KJ, 0, false>(h, a, false, st);
-    if (a.rule == JSS_RULE_RANDOM) return launch_step_variant<KJ, 1, false>(h, a, false, st);
-    return launch_step_variant<KJ, 2, false>(h, a, rem, st);
+    const int kj = kj_of(h->insts[h->p.uniform_inst].J);
+#define JSS_STEP_UNI(KJ_)                                                               \
+    do {                                                                                \
+        if (sample == 0) return launch_step_uniform<KJ_, 0>(h, a, false, st);           \
+        if (sample == 1) return launch_step_uniform<KJ_, 1>(h, a, false, st);           \
+        return launch_step_uniform<KJ_, 2>(h, a, rem, st);                              \
+    } while (0)
+    if (kj == 1) JSS_STEP_UNI(1);
+    if (kj == 2) JSS_STEP_UNI(2);
+    JSS_STEP_UNI(4);
+#undef JSS_STEP_UNI
 }
 
 template <int KJ, int MODE>
@@ -176,7 +241,6 @@ template <int KJ>
 int launch_class(jss_t *h, const JssLaunch &a, const JssSmemLayout &sl, cudaStream_t st) {
     if (a.tile_end - a.tile_begin <= 0) return JSS_OK;
     switch (a.mode) {
-    case JSS_MODE_STEP: return launch_step<KJ>(h, a, st);
     case JSS_MODE_POLICY: return launch_variant<KJ, JSS_MODE_POLICY>(h, a, sl, st);
     case JSS_MODE_ROLLOUT: return launch_variant<KJ, JSS_MODE_ROLLOUT>(h, a, sl, st);
     default: return launch_variant<KJ, JSS_MODE_RESET>(h, a, sl, st);   // reset / export / import
@@ -184,6 +248,7 @@ int launch_class(jss_t *h, const JssLaunch &a, const JssSmemLayout &sl, cudaStre
 }
 
 int launch_all(jss_t *h, JssLaunch a, bool want_rem, cudaStream_t st) {
+    if (a.mode == JSS_MODE_STEP) return launch_step(h, a, st);   // one launch, whatever the mix of lane classes
     const JssSmemLayout &sl = want_rem ? h->sl_rem : h->sl_norem;
     for (int c = 0; c < 3; c++) {
         a.tile_begin = h->class_tile_begin[c];
@@ -369,22 +434,29 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
         ops_max = std::max(ops_max, h->insts[k].J * h->insts[k].M);
         rem_max = std::max(rem_max, h->insts[k].J * (h->insts[k].M + 1));
     }
-    // group envs by (KJ class, instance) -> tiles of <= JSS_WARPS_PER_CTA envs of one instance
+    // group envs by (KJ class, instance) -> tiles of <= JSS_WARPS_PER_CTA envs of one instance.  The most
+    // expensive lane class (KJ = 4) comes first: the mixed-batch step kernel hands the tile list out front to
+    // back, so the cheap 15..30-job envs fill the tail (longest processing time first).
     std::vector<int32_t> order(N);
     for (int e = 0; e < N; e++) order[e] = e;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
         const int ka = env_to_inst[a], kb = env_to_inst[b];
         const int ca = class_of(kj_of(h->insts[ka].J)), cb = class_of(kj_of(h->insts[kb].J));
-        if (ca != cb) return ca < cb;
+        if (ca != cb) return ca > cb;
         return ka < kb;
     });
     std::vector<JssTile> tiles;
+    std::vector<uint32_t> state_off16((size_t)N), hdr_off16((size_t)N);
+    std::vector<double> tile_cost;
     for (int c = 0; c < 3; c++) h->class_tile_begin[c] = h->class_tile_end[c] = 0;
     int pos = 0;
     int cur_class = -1;
+    uint64_t off16 = 0;                                  // running state offset in 16-byte units
     while (pos < N) {
         const int k = env_to_inst[order[pos]];
         const int c = class_of(kj_of(h->insts[k].J));
+        const int Jc = round_up(h->insts[k].J, 4), Mc = round_up(h->insts[k].M, 4);
+        const uint32_t block16 = (uint32_t)(5 * Jc + Mc + 12) / 4;
         int end = pos;
         while (end < N && env_to_inst[order[end]] == k) end++;
         if (c != cur_class) {
@@ -394,13 +466,45 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
         }
         for (int f = pos; f < end; f += JSS_WARPS_PER_CTA) {
             JssTile t;
+            const int cnt = std::min(JSS_WARPS_PER_CTA, end - f);
             t.first = f;
-            t.inst_count = (k << 8) | std::min(JSS_WARPS_PER_CTA, end - f);
+            t.inst_count = (k << 8) | cnt;
+            t.state_off16 = (uint32_t)off16;
+            t.block16 = block16;
+            for (int w = 0; w < cnt; w++) {
+                state_off16[order[f + w]] = (uint32_t)(off16 + (uint64_t)w * block16);
+                hdr_off16[order[f + w]] = (uint32_t)(off16 + (uint64_t)w * block16) + (uint32_t)(5 * Jc + Mc + 8) / 4;
+            }
+            off16 += (uint64_t)cnt * block16;
             tiles.push_back(t);
+            // relative cost of an env-step: measured on uniform batches it is ~linear in J (issue-bound kernel)
+            tile_cost.push_back(cnt * (40.0 + h->insts[k].J));
         }
         pos = end;
     }
     if (cur_class >= 0) h->class_tile_end[cur_class] = (int)tiles.size();
+    if (off16 >= (1ull << 32)) return fail(h, JSS_ERR_UNSUPPORTED, "state exceeds 64 GiB");
+    const size_t state_words = (size_t)off16 * 4;
+
+    // chunks for the mixed-batch step kernel: runs of consecutive tiles of one lane class with about equal cost,
+    // ~6 per resident CTA, so that drawing them by ticket balances the SMs whatever the instance mix is
+    std::vector<JssChunk> chunks;
+    {
+        double total = 0;
+        for (double c : tile_cost) total += c;
+        const double target = total / std::max(1, h->sm_count * JSS_MIN_CTAS * 6);
+        for (int c = 2; c >= 0; c--) {
+            int t = h->class_tile_begin[c];
+            const int te = h->class_tile_end[c];
+            while (t < te) {
+                double acc = 0;
+                int e = t;
+                while (e < te && (e == t || acc + tile_cost[e] <= target)) acc += tile_cost[e++];
+                chunks.push_back(JssChunk{t, e, c == 0 ? 1 : (c == 1 ? 2 : 4), 0});
+                t = e;
+            }
+        }
+    }
 
     JssParams &p = h->p;
     p.n_envs = N;
@@ -408,7 +512,7 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
     p.machines_max = mmax;
     p.Jcap = round_up(jmax, 4);
     p.Mcap = round_up(mmax, 4);
-    p.block_words = 5 * p.Jcap + p.Mcap + 12;
+    p.block_words = 5 * p.Jcap + p.Mcap + 12;            // batch maximum: sizes the shared-memory staging buffers
     p.mask_stride = round_up(jmax + 1, 4);
     p.create_flags = (int32_t)h->create_flags;
     p.env_id_base = h->env_id_base;
@@ -431,14 +535,28 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
     int rc;
     int32_t *d_order = nullptr;
     JssTile *d_tiles = nullptr;
+    JssChunk *d_chunks = nullptr;
+    uint32_t *d_soff = nullptr, *d_hoff = nullptr;
     if ((rc = dev_alloc(h, &d_order, (size_t)N))) return rc;
     if ((rc = dev_alloc(h, &d_tiles, tiles.size()))) return rc;
+    if ((rc = dev_alloc(h, &d_chunks, chunks.size()))) return rc;
+    if ((rc = dev_alloc(h, &d_soff, (size_t)N))) return rc;
+    if ((rc = dev_alloc(h, &d_hoff, (size_t)N))) return rc;
+    if ((rc = dev_alloc(h, &p.ticket, (size_t)4))) return rc;       // zero-initialised
     JSS_CUDA(h, cudaMemcpy(d_order, order.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
     JSS_CUDA(h, cudaMemcpy(d_tiles, tiles.data(), tiles.size() * sizeof(JssTile), cudaMemcpyHostToDevice));
+    JSS_CUDA(h, cudaMemcpy(d_chunks, chunks.data(), chunks.size() * sizeof(JssChunk), cudaMemcpyHostToDevice));
+    JSS_CUDA(h, cudaMemcpy(d_soff, state_off16.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
+    JSS_CUDA(h, cudaMemcpy(d_hoff, hdr_off16.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
     p.order = d_order;
     p.tiles = d_tiles;
+    p.chunks = d_chunks;
+    p.n_chunks = (int32_t)chunks.size();
+    p.state_off16 = d_soff;
+    p.hdr_off16 = d_hoff;
+    h->ticket_parity = 0;
     const size_t NJ = (size_t)N * jmax, NM = (size_t)N * mmax;
-    if ((rc = dev_alloc(h, &p.state, (size_t)N * p.block_words))) return rc;
+    if ((rc = dev_alloc(h, &p.state, state_words))) return rc;
     if ((rc = dev_alloc(h, &p.mask, (size_t)N * p.mask_stride))) return rc;
     if ((rc = dev_alloc(h, &p.obs, NJ * 7))) return rc;
     if ((rc = dev_alloc(h, &p.scalars, (size_t)N * 4))) return rc;

@@ -183,7 +183,7 @@ JSS_DEV void env_clear_jobs(const InstView &iv, EnvRegs<KJ> &s) {
 
 template <int KJ>
 JSS_DEV void env_load_from(const JssParams &p, const InstView &iv, const int32_t *blk, int lane, EnvRegs<KJ> &s) {
-    const int Jc = p.Jcap;
+    const int Jc = iv.si->Jcap, Mc = iv.si->Mcap;   // geometry of the env's own instance
     if (KJ * lane < iv.si->J) {
         const int32_t *q = blk + KJ * lane;
         jss_ld<KJ>(q, s.todo);
@@ -196,14 +196,16 @@ JSS_DEV void env_load_from(const JssParams &p, const InstView &iv, const int32_t
     }
     const int32_t *tail = blk + 5 * Jc;
     s.tuam = (lane < iv.si->M) ? tail[lane] : 0;
-    s.lb = reinterpret_cast<const uint8_t *>(tail + p.Mcap)[lane];
-    const int4 h4 = *reinterpret_cast<const int4 *>(tail + p.Mcap + 8);
+    s.lb = reinterpret_cast<const uint8_t *>(tail + Mc)[lane];
+    const int4 h4 = *reinterpret_cast<const int4 *>(tail + Mc + 8);
     s.t = h4.x; s.flags = (uint32_t)h4.y; s.ep_steps = h4.z; s.ep_return = h4.w;
     env_derive_ops<KJ>(iv, s, lane);
 }
+// start of env's state block (blocks are stored in tile order with per-instance sizes, see JssTile)
+JSS_DEV int32_t *env_block(const JssParams &p, int env) { return p.state + (size_t)p.state_off16[env] * 4; }
 template <int KJ>
 JSS_DEV void env_load(const JssParams &p, const InstView &iv, int env, int lane, EnvRegs<KJ> &s) {
-    env_load_from<KJ>(p, iv, p.state + (size_t)env * p.block_words, lane, s);
+    env_load_from<KJ>(p, iv, env_block(p, env), lane, s);
 }
 
 // policy kernels read only what the rule looks at: bits + header always, todo for every
@@ -211,8 +213,8 @@ JSS_DEV void env_load(const JssParams &p, const InstView &iv, int env, int lane,
 template <int KJ>
 JSS_DEV void env_load_for_policy(const JssParams &p, const InstView &iv, int env, int lane, EnvRegs<KJ> &s,
                                  int rule) {
-    const int32_t *blk = p.state + (size_t)env * p.block_words;
-    const int Jc = p.Jcap;
+    const int32_t *blk = env_block(p, env);
+    const int Jc = iv.si->Jcap, Mc = iv.si->Mcap;
     env_clear_jobs<KJ>(iv, s);
     if (rule != JSS_RULE_RANDOM && KJ * lane < iv.si->J) {
         jss_ld<KJ>(blk + KJ * lane, s.todo);
@@ -220,8 +222,8 @@ JSS_DEV void env_load_for_policy(const JssParams &p, const InstView &iv, int env
     }
     s.tuam = 0;
     const int32_t *tail = blk + 5 * Jc;
-    s.lb = reinterpret_cast<const uint8_t *>(tail + p.Mcap)[lane];
-    const int4 h4 = *reinterpret_cast<const int4 *>(tail + p.Mcap + 8);
+    s.lb = reinterpret_cast<const uint8_t *>(tail + Mc)[lane];
+    const int4 h4 = *reinterpret_cast<const int4 *>(tail + Mc + 8);
     s.t = h4.x; s.flags = (uint32_t)h4.y; s.ep_steps = h4.z; s.ep_return = h4.w;
     if (rule != JSS_RULE_RANDOM) env_derive_ops<KJ>(iv, s, lane);
     else {
@@ -232,7 +234,7 @@ JSS_DEV void env_load_for_policy(const JssParams &p, const InstView &iv, int env
 
 template <int KJ>
 JSS_DEV void env_store_to(const JssParams &p, const InstView &iv, int32_t *blk, int lane, const EnvRegs<KJ> &s) {
-    const int Jc = p.Jcap;
+    const int Jc = iv.si->Jcap, Mc = iv.si->Mcap;
     if (KJ * lane < Jc) {       // lanes past the last job hold the "finished job" padding values: the whole block is defined
         int32_t *q = blk + KJ * lane;
         jss_st<KJ>(q, s.todo);
@@ -242,10 +244,10 @@ JSS_DEV void env_store_to(const JssParams &p, const InstView &iv, int32_t *blk, 
         jss_st<KJ>(q + 4 * Jc, s.col4);
     }
     int32_t *tail = blk + 5 * Jc;
-    if (lane < p.Mcap) tail[lane] = (lane < iv.si->M) ? s.tuam : 0;
-    reinterpret_cast<uint8_t *>(tail + p.Mcap)[lane] = (uint8_t)s.lb;
+    if (lane < Mc) tail[lane] = (lane < iv.si->M) ? s.tuam : 0;
+    reinterpret_cast<uint8_t *>(tail + Mc)[lane] = (uint8_t)s.lb;
     if (lane == 0)
-        *reinterpret_cast<int4 *>(tail + p.Mcap + 8) = make_int4(s.t, (int)s.flags, s.ep_steps, s.ep_return);
+        *reinterpret_cast<int4 *>(tail + Mc + 8) = make_int4(s.t, (int)s.flags, s.ep_steps, s.ep_return);
 }
 
 template <int KJ>
@@ -254,7 +256,7 @@ JSS_DEV void env_store(const JssParams &p, const InstView &iv, int env, int lane
     // before any lane overwrites the block: paths such as the auto-reset have no
     // collective between load and store
     __syncwarp();
-    env_store_to<KJ>(p, iv, p.state + (size_t)env * p.block_words, lane, s);
+    env_store_to<KJ>(p, iv, env_block(p, env), lane, s);
 }
 
 // jss_env.py:145-181
@@ -766,6 +768,7 @@ JSS_DEV void jss_stage_instance(const JssParams &p, const JssInstDesc &d, SmInst
         si->f_mto = (float)d.max_time_op; si->f_mtj = (float)d.max_time_jobs; si->f_sop = (float)d.sum_op;
         si->f_M = (float)d.M;
         si->r_mto = d.r_mto; si->r_mtj = d.r_mtj; si->r_sop = d.r_sop; si->r_M = d.r_M;
+        si->Jcap = (d.J + 3) & ~3; si->Mcap = (d.M + 3) & ~3; si->block_words = 5 * si->Jcap + si->Mcap + 12;
     }
     if (!want_tables) return;
     {   // pools are padded so whole uint4 copies stay in-bounds
@@ -846,7 +849,7 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
             env_emit_all<KJ>(p, iv, s, env, lane, scratch, raw);
         } else if (s.flags != flags_in) {                // only the sticky error bit changed
             if (lane == 0) {
-                p.state[(size_t)env * p.block_words + 5 * p.Jcap + p.Mcap + 8 + JSS_HDR_FLAGS] = (int32_t)s.flags;
+                p.state[(size_t)p.hdr_off16[env] * 4 + JSS_HDR_FLAGS] = (int32_t)s.flags;
                 reinterpret_cast<int4 *>(p.scalars)[env] =
                     make_int4(0, 0, s.t, (int)((s.flags << 8) | (s.flags & JSS_FLAG_DONE)));
             }
@@ -872,9 +875,8 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
     }
 }
 
-template <bool UNI = false>
 JSS_DEV void jss_tile_desc(const JssParams &p, int tile, int &first, int &inst, int &count) {
-    if (UNI || p.uniform_inst >= 0) {    // one instance, identity order: no descriptor loads
+    if (p.uniform_inst >= 0) {           // one instance, identity order: no descriptor loads
         first = tile * JSS_WARPS_PER_CTA;
         inst = p.uniform_inst;
         count = min(JSS_WARPS_PER_CTA, p.n_envs - first);
@@ -882,18 +884,6 @@ JSS_DEV void jss_tile_desc(const JssParams &p, int tile, int &first, int &inst, 
         const JssTile td = p.tiles[tile];
         first = td.first; inst = td.inst_count >> 8; count = td.inst_count & 255;
     }
-}
-template <bool UNI = false>
-JSS_DEV int jss_tile_env(const JssParams &p, int tile, int tile_end, int warp) {
-    if (UNI) {                           // env = 8 * tile + warp, nothing to load
-        const int e = tile * JSS_WARPS_PER_CTA + warp;
-        return (tile < tile_end && e < p.n_envs) ? e : -1;
-    }
-    if (tile >= tile_end) return -1;
-    int first, inst, count;
-    jss_tile_desc(p, tile, first, inst, count);
-    if (warp >= count) return -1;
-    return p.uniform_inst >= 0 ? first + warp : p.order[first + warp];
 }
 
 #ifndef JSS_MIN_CTAS
@@ -932,15 +922,148 @@ jss_env_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     }
 }
 
-// ---- the hot kernel: fused step with TMA prefetch ------------------------------------------------
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// The step kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the NEXT
+// launch's CTAs may become resident (and run their prologue: shared-memory carve-up, mbarrier init,
+// staging of the read-only instance tables) while this launch drains; jss_pdl_wait() blocks them until
+// every memory operation of the preceding grid is visible, so nothing mutable is touched before it.
+#ifndef JSS_EMU
+JSS_DEV void jss_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+JSS_DEV void jss_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#else
+JSS_DEV void jss_pdl_launch_dependents() {}
+JSS_DEV void jss_pdl_wait() {}
+#endif
+
+// ---- the hot kernels: fused step with TMA prefetch ---------------------------------------------
 // Persistent CTAs (grid = SMs x resident CTAs), one warp per env of a tile.  Per warp in shared
 // memory: an mbarrier, a state-block buffer that receives the NEXT env's block by cp.async.bulk
-// while the current env is simulated, and the observation staging buffer that leaves by bulk store.
-// SAMPLE = true additionally picks every env's NEXT action (masked-uniform sampler or a
-// dispatching rule) from the freshly computed state, so a policy-driven loop is one launch per step.
-// UNI = true (every env runs the same instance): the per-instance scalars are read from the kernel
-// parameters (constant bank operands) instead of shared memory.
-template <int KJ, int SAMPLE, bool UNI>   // SAMPLE 0: step only, 1: + masked-uniform sampler, 2: + any dispatching rule
+// while the current env is simulated, and the staging buffers (new state block, observation rows)
+// that leave by bulk store.
+// SAMPLE = 1 / 2 additionally picks every env's NEXT action (masked-uniform sampler / any dispatching
+// rule) from the freshly computed state, so a policy-driven loop is one launch per step.
+struct JssWarpSmem {        // per-warp shared-memory regions of the step kernels
+    int32_t *state_in, *state_out;
+    float *scratch;
+    jss_saddr_t mbar, state_sa, scratch_sa, state_out_sa;
+};
+
+// env handled by `warp` in `tile` (-1: none) and where its state block lives (16-byte units)
+template <bool UNI>
+JSS_DEV int jss_tile_env(const JssParams &p, const SmInst *uni, int tile, int tile_end, int warp, uint32_t &off16,
+                         uint32_t &blk16) {
+    if (UNI) {                           // env = 8 * tile + warp, block = env * block_words: nothing to load
+        const int e = tile * JSS_WARPS_PER_CTA + warp;
+        blk16 = (uint32_t)uni->block_words >> 2;
+        off16 = (uint32_t)e * blk16;
+        return (tile < tile_end && e < p.n_envs) ? e : -1;
+    }
+    if (tile >= tile_end) return -1;
+    const int4 td = *reinterpret_cast<const int4 *>(p.tiles + tile);     // JssTile, one 16-byte load
+    if (warp >= (td.y & 255)) return -1;
+    blk16 = (uint32_t)td.w;
+    off16 = (uint32_t)td.z + (uint32_t)warp * blk16;
+    return p.order[td.x + warp];
+}
+
+// where the state block of warp `warp` of `tile` lives (16-byte units); recomputed after the step instead of
+// being carried in registers across it
+template <bool UNI>
+JSS_DEV void jss_tile_state(const JssParams &p, const SmInst *uni, int tile, int warp, uint32_t &off16, uint32_t &blk16) {
+    if (UNI) {
+        blk16 = (uint32_t)uni->block_words >> 2;
+        off16 = (uint32_t)(tile * JSS_WARPS_PER_CTA + warp) * blk16;
+    } else {
+        const int4 td = *reinterpret_cast<const int4 *>(p.tiles + tile);
+        blk16 = (uint32_t)td.w;
+        off16 = (uint32_t)td.z + (uint32_t)warp * blk16;
+    }
+}
+
+// tiles tile, tile + tile_step, ... < tile_end of ONE lane class through the prefetch pipeline
+template <int KJ, int SAMPLE, bool UNI>
+JSS_DEV void jss_step_tiles(const JssParams &p, const JssLaunch &a, const JssSmemLayout &sl, InstView &iv, SmInst *si,
+                            uint16_t *sm_ops, int32_t *sm_len, uint16_t *sm_rem, const JssWarpSmem &w, int warp,
+                            int lane, int tile, int tile_end, int tile_step, int &staged, uint32_t &phase) {
+    int env_next, act_next = 0;
+    {
+        uint32_t off16, blk16;
+        env_next = jss_tile_env<UNI>(p, &a.uni, tile, tile_end, warp, off16, blk16);
+        if (env_next >= 0) {
+            if (lane == 0) jss_bulk_load(w.state_sa, p.state + (size_t)off16 * 4, blk16 * 16u, w.mbar);
+            act_next = a.actions[env_next];
+        }
+    }
+    for (; tile < tile_end; tile += tile_step) {
+        if (!UNI) {
+            const int inst = p.tiles[tile].inst_count >> 8;
+            if (inst != staged) {                        // CTA-uniform
+                __syncthreads();
+                jss_stage_instance(p, p.inst[inst], si, sm_ops, sm_len, sm_rem, SAMPLE == 2 && sl.rem_elems > 0);
+                staged = inst;
+                __syncthreads();
+            }
+        }
+        const int env = env_next, action = act_next;
+        EnvRegs<KJ> s;
+        if (env >= 0) {
+            jss_mbar_wait(w.mbar, phase);                // this env's block has landed in shared memory
+            phase ^= 1u;
+            env_load_from<KJ>(p, iv, w.state_in, lane, s);
+            __syncwarp();                                // every lane has read the buffer
+        }
+        {   // prefetch the next env's block + action
+            uint32_t off16, blk16;
+            env_next = jss_tile_env<UNI>(p, &a.uni, tile + tile_step, tile_end, warp, off16, blk16);
+            if (env_next >= 0) {
+                if (lane == 0) jss_bulk_load(w.state_sa, p.state + (size_t)off16 * 4, blk16 * 16u, w.mbar);
+                act_next = a.actions[env_next];
+            }
+        }
+        if (env < 0) continue;
+        int raw = 0;
+        const uint32_t flags_in = s.flags;
+        // the previous env's observation must have left the staging buffer (also aliased by hz)
+        if (lane == 0) jss_bulk_store_wait_read();
+        __syncwarp();
+        const bool changed = env_step<KJ>(p, iv, s, env, lane, action, raw, reinterpret_cast<int *>(w.scratch));
+        if (SAMPLE) {
+            const uint32_t h = jss_hash3(a.seed, p.env_id_base + (uint64_t)env, a.step_index);
+            const int nxt = env_select_action<KJ, SAMPLE == 1>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
+            if (lane == 0) a.actions_out[env] = nxt;
+        }
+        if (changed) {
+            // new state -> shared staging -> one bulk store (every word of the block is rewritten)
+            env_store_to<KJ>(p, iv, w.state_out, lane, s);
+            uint32_t off16, blk16;
+            jss_tile_state<UNI>(p, &a.uni, tile, warp, off16, blk16);
+            env_emit_all<KJ, true>(p, iv, s, env, lane, w.scratch, raw, w.scratch_sa,
+                                   p.state + (size_t)off16 * 4, w.state_out_sa, blk16 * 16u);
+        } else if (s.flags != flags_in) {                // only the sticky error bit changed
+            if (lane == 0) {
+                p.state[(size_t)p.hdr_off16[env] * 4 + JSS_HDR_FLAGS] = (int32_t)s.flags;
+                reinterpret_cast<int4 *>(p.scalars)[env] =
+                    make_int4(0, 0, s.t, (int)((s.flags << 8) | (s.flags & JSS_FLAG_DONE)));
+            }
+        }
+    }
+}
+
+JSS_DEV void jss_step_carve(const JssSmemLayout &sl, char *sm, int warp, JssWarpSmem &w) {
+    char *wbase = sm + sl.off_warp0 + warp * sl.warp_stride;
+    w.state_in = reinterpret_cast<int32_t *>(wbase + 16);
+    w.scratch = reinterpret_cast<float *>(wbase + sl.off_scratch);
+    w.mbar = jss_saddr(sm) + (sl.off_warp0 + warp * sl.warp_stride);   // shared-space addresses
+    w.state_sa = w.mbar + 16;
+    w.scratch_sa = w.mbar + sl.off_scratch;
+    // state-out staging sits right behind the observation staging (both leave by bulk store)
+    w.state_out = reinterpret_cast<int32_t *>(w.scratch + sl.scratch_words);
+    w.state_out_sa = w.scratch_sa + sl.scratch_words * 4;
+}
+
+// Uniform batch (every env runs the same instance): static strided tiles, the per-instance scalars are
+// read from the kernel parameters (constant-bank operands), no CTA barrier after the first staging.
+template <int KJ, int SAMPLE>
 __global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, JSS_MIN_CTAS)
 jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JSS_SMEM_DECL(jss_smem);
@@ -950,85 +1073,64 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     int32_t *sm_len = reinterpret_cast<int32_t *>(sm + sl.off_len);
     uint16_t *sm_rem = reinterpret_cast<uint16_t *>(sm + sl.off_rem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    char *wbase = sm + sl.off_warp0 + warp * sl.warp_stride;
-    int32_t *state_in = reinterpret_cast<int32_t *>(wbase + 16);
-    float *scratch = reinterpret_cast<float *>(wbase + sl.off_scratch);
-    const jss_saddr_t mbar = jss_saddr(sm) + (sl.off_warp0 + warp * sl.warp_stride);   // shared-space addresses
-    const jss_saddr_t state_sa = mbar + 16, scratch_sa = mbar + sl.off_scratch;
-    // state-out staging sits right behind the observation staging (both leave by bulk store)
-    int32_t *state_out = reinterpret_cast<int32_t *>(scratch + sl.scratch_words);
-    const jss_saddr_t state_out_sa = scratch_sa + sl.scratch_words * 4;
-    const uint32_t blk_bytes = (uint32_t)p.block_words * 4u;
-    if (lane == 0) jss_mbar_init(mbar);
-    __syncwarp();
+    JssWarpSmem w;
+    jss_step_carve(sl, sm, warp, w);
+    if (lane == 0) jss_mbar_init(w.mbar);
     InstView iv;
-    iv.ops = sm_ops; iv.len = sm_len; iv.rem = sm_rem; iv.si = UNI ? &a.uni : si;
-    int staged = -1;
+    iv.ops = sm_ops; iv.len = sm_len; iv.rem = sm_rem; iv.si = &a.uni;
+    jss_pdl_launch_dependents();
+    // prologue on read-only data (overlaps the tail of the previous launch under PDL)
+    jss_stage_instance(p, p.inst[p.uniform_inst], si, sm_ops, sm_len, sm_rem, SAMPLE == 2 && sl.rem_elems > 0);
+    __syncthreads();
+    jss_pdl_wait();
+    int staged = p.uniform_inst;
     uint32_t phase = 0;
     // Static strided tiles; the env after the current one is known one iteration ahead, which is what
-    // the TMA prefetch needs.  (A per-warp ticket counter for dynamic balancing was measured and was
-    // not faster: 109.4 vs 107.4 us per launch, profiles/r01_notes.md.)
-    // Uniform batches: tiles strided over the CTAs.  Mixed batches: each CTA owns a CONTIGUOUS range of
-    // the (instance-sorted) tiles, so it re-stages instance tables once or twice instead of per tile.
-    int tile, tile_end, tile_step;
-    if (UNI) {
-        tile = a.tile_begin + (int)blockIdx.x; tile_end = a.tile_end; tile_step = (int)gridDim.x;
-    } else {
-        const int per = (a.tile_end - a.tile_begin + (int)gridDim.x - 1) / (int)gridDim.x;
-        tile = a.tile_begin + (int)blockIdx.x * per; tile_end = min(tile + per, a.tile_end); tile_step = 1;
-    }
-    int env_next = jss_tile_env<UNI>(p, tile, tile_end, warp);
-    int act_next = 0;
-    if (env_next >= 0) {
-        if (lane == 0) jss_bulk_load(state_sa, p.state + (size_t)env_next * p.block_words, blk_bytes, mbar);
-        act_next = a.actions[env_next];
-    }
-    for (; tile < tile_end; tile += tile_step) {
-        int first, inst, count;
-        jss_tile_desc<UNI>(p, tile, first, inst, count);
-        if (inst != staged) {                            // CTA-uniform
-            __syncthreads();
-            jss_stage_instance(p, p.inst[inst], si, sm_ops, sm_len, sm_rem, SAMPLE == 2 && sl.rem_elems > 0);
-            staged = inst;
-            __syncthreads();
-        }
-        const int env = env_next, action = act_next;
-        env_next = jss_tile_env<UNI>(p, tile + tile_step, tile_end, warp);
-        EnvRegs<KJ> s;
-        if (env >= 0) {
-            jss_mbar_wait(mbar, phase);                  // this env's block has landed in shared memory
-            phase ^= 1u;
-            env_load_from<KJ>(p, iv, state_in, lane, s);
-            __syncwarp();                                // every lane has read the buffer
-        }
-        if (env_next >= 0) {                             // prefetch the next env's block + action
-            if (lane == 0) jss_bulk_load(state_sa, p.state + (size_t)env_next * p.block_words, blk_bytes, mbar);
-            act_next = a.actions[env_next];
-        }
-        if (env < 0) continue;
-        int raw = 0;
-        const uint32_t flags_in = s.flags;
-        // the previous env's observation must have left the staging buffer (also aliased by hz)
-        if (lane == 0) jss_bulk_store_wait_read();
-        __syncwarp();
-        const bool changed = env_step<KJ>(p, iv, s, env, lane, action, raw, reinterpret_cast<int *>(scratch));
-        if (SAMPLE) {
-            const uint32_t h = jss_hash3(a.seed, p.env_id_base + (uint64_t)env, a.step_index);
-            const int nxt = env_select_action<KJ, SAMPLE == 1>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
-            if (lane == 0) a.actions_out[env] = nxt;
-        }
-        if (changed) {
-            // new state -> shared staging -> one bulk store (every word of the block is rewritten)
-            env_store_to<KJ>(p, iv, state_out, lane, s);
-            env_emit_all<KJ, true>(p, iv, s, env, lane, scratch, raw, scratch_sa,
-                                   p.state + (size_t)env * p.block_words, state_out_sa, blk_bytes);
-        } else if (s.flags != flags_in) {                // only the sticky error bit changed
-            if (lane == 0) {
-                p.state[(size_t)env * p.block_words + 5 * p.Jcap + p.Mcap + 8 + JSS_HDR_FLAGS] = (int32_t)s.flags;
-                reinterpret_cast<int4 *>(p.scalars)[env] =
-                    make_int4(0, 0, s.t, (int)((s.flags << 8) | (s.flags & JSS_FLAG_DONE)));
-            }
-        }
+    // the TMA prefetch needs.
+    jss_step_tiles<KJ, SAMPLE, true>(p, a, sl, iv, si, sm_ops, sm_len, sm_rem, w, warp, lane,
+                                     a.tile_begin + (int)blockIdx.x, a.tile_end, (int)gridDim.x, staged, phase);
+    if (lane == 0) jss_bulk_store_wait_all();            // shared memory must outlive the bulk reads
+}
+
+// Mixed batch: ONE persistent launch covers the three lane classes.  The host cuts the (class, instance)-sorted
+// tile list into chunks of roughly equal cost, most expensive class first; CTAs draw chunks by ticket (longest
+// processing time first), so a 15-job env costs what a 15-job env costs and the tail is filled with cheap work.
+// Launch k draws from ticket[k & 1] and zeroes ticket[(k + 1) & 1] for its successor (which cannot start
+// drawing before this grid has completed: jss_pdl_wait).
+template <int SAMPLE>
+__global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, JSS_MIN_CTAS)
+jss_step_mixed_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
+    JSS_SMEM_DECL(jss_smem);
+    char *sm = reinterpret_cast<char *>(jss_smem);
+    SmInst *si = reinterpret_cast<SmInst *>(sm);
+    uint16_t *sm_ops = reinterpret_cast<uint16_t *>(sm + sizeof(SmInst));
+    int32_t *sm_len = reinterpret_cast<int32_t *>(sm + sl.off_len);
+    uint16_t *sm_rem = reinterpret_cast<uint16_t *>(sm + sl.off_rem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    JssWarpSmem w;
+    jss_step_carve(sl, sm, warp, w);
+    int *s_chunk = reinterpret_cast<int *>(sm + sl.off_warp0 - 16);     // 16 spare bytes in front of the warp regions
+    if (lane == 0) jss_mbar_init(w.mbar);
+    InstView iv;
+    iv.ops = sm_ops; iv.len = sm_len; iv.rem = sm_rem; iv.si = si;
+    jss_pdl_launch_dependents();
+    jss_pdl_wait();
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.ticket[a.ticket_parity ^ 1] = 0u;
+    int staged = -1;
+    uint32_t phase = 0;
+    for (;;) {
+        __syncthreads();                                 // all warps are done with the previous chunk
+        if (threadIdx.x == 0) *s_chunk = (int)atomicAdd(&p.ticket[a.ticket_parity], 1u);
+        __syncthreads();
+        const int c = *s_chunk;
+        if (c >= p.n_chunks) break;
+        const int4 ch = *reinterpret_cast<const int4 *>(p.chunks + c);   // JssChunk
+        if (ch.z == 4)
+            jss_step_tiles<4, SAMPLE, false>(p, a, sl, iv, si, sm_ops, sm_len, sm_rem, w, warp, lane, ch.x, ch.y, 1, staged, phase);
+        else if (ch.z == 2)
+            jss_step_tiles<2, SAMPLE, false>(p, a, sl, iv, si, sm_ops, sm_len, sm_rem, w, warp, lane, ch.x, ch.y, 1, staged, phase);
+        else
+            jss_step_tiles<1, SAMPLE, false>(p, a, sl, iv, si, sm_ops, sm_len, sm_rem, w, warp, lane, ch.x, ch.y, 1, staged, phase);
     }
     if (lane == 0) jss_bulk_store_wait_all();            // shared memory must outlive the bulk reads
 }
@@ -1049,7 +1151,7 @@ __global__ void jss_stats_kernel(const JssParams p, unsigned long long *out) {
     unsigned long long mn = ~0ull, mx = 0;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < p.n_envs; e += gridDim.x * blockDim.x) {
         const int64_t *acc = p.acc + (size_t)e * 4;
-        const int32_t *hdr = p.state + (size_t)e * p.block_words + 5 * p.Jcap + p.Mcap + 8;
+        const int32_t *hdr = p.state + (size_t)p.hdr_off16[e] * 4;
         ep += (unsigned long long)p.episode_count[e];
         steps += (unsigned long long)acc[0] + (unsigned long long)(((uint32_t)hdr[JSS_HDR_FLAGS] & JSS_FLAG_DONE) ? 0 : hdr[JSS_HDR_EP_STEPS]);
         smk += (unsigned long long)acc[1];

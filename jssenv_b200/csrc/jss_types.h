@@ -30,6 +30,7 @@ struct JssInstDesc {
 //   then 8 words  = 32 bytes, byte l = lane l's job bits: bit i legal(job KJ*l+i),
 //                   bit 4+i blocked by a no-op (action_illegal_no_op)
 //        4 words  header: current_time_step, flags, episode_steps, episode_return_raw
+// Jcap / Mcap are those of the ENV'S OWN instance (J, M rounded up to a multiple of 4), not batch maxima.
 // Not stored because derivable: event queue, illegal_actions
 // [M][J], machine_legal, both counters, needed_machine_jobs, total_perform_op_time_jobs.
 #define JSS_HDR_T 0
@@ -37,13 +38,24 @@ struct JssInstDesc {
 #define JSS_HDR_EP_STEPS 2
 #define JSS_HDR_EP_RETURN 3
 
-struct JssTile {       // one CTA work item: up to `count` envs of ONE instance
+struct JssTile {       // one CTA work item: up to `count` envs of ONE instance (one 16-byte load)
     int32_t first;     // index into `order`
     int32_t inst_count;  // (instance << 8) | count
+    // The state blocks are stored in TILE order with the block size of the env's own instance (a mixed batch
+    // moves 432 B for a 15x15 env and 2 128 B for a 100x20 env, not the batch maximum): warp w of this tile
+    // owns the block at 16-byte unit  state_off16 + w * block16.
+    uint32_t state_off16;
+    uint32_t block16;  // block size of this tile's instance in 16-byte units
+};
+
+struct JssChunk {      // mixed batches: a run of consecutive tiles of ONE lane class, handed out by ticket
+    int32_t tile_begin, tile_end;
+    int32_t kj;        // 1, 2 or 4 jobs per lane
+    int32_t pad_;
 };
 
 struct JssParams {
-    int32_t n_envs, Jcap, Mcap, block_words;
+    int32_t n_envs, Jcap, Mcap, block_words;   // Jcap / Mcap / block_words: batch maxima (shared-memory sizing only)
     int32_t jobs_max, machines_max, mask_stride, create_flags;
     int32_t uniform_inst;    // >= 0: every env runs this instance and `order` is the identity
     uint64_t env_id_base;
@@ -53,7 +65,12 @@ struct JssParams {
     const uint16_t *rem_pool;
     const int32_t *order;    // env ids grouped by (KJ class, instance)
     const JssTile *tiles;
-    int32_t *state;          // [N][block_words]
+    const JssChunk *chunks;  // mixed-batch step kernel: work list, most expensive lane class first
+    int32_t n_chunks;
+    uint32_t *ticket;        // [2] chunk tickets; launch k draws from ticket[k & 1] and zeroes ticket[(k + 1) & 1]
+    const uint32_t *state_off16;   // per env: start of its state block, in 16-byte units (tile order, see JssTile)
+    const uint32_t *hdr_off16;     // per env: start of its 4-word header (t, flags, episode steps / return), 16-byte units
+    int32_t *state;          // per-env blocks of 5 * Jcap_i + Mcap_i + 12 words (Jcap_i, Mcap_i: the env's instance)
     uint8_t *mask;           // [N][mask_stride]
     float *obs;              // [N][jobs_max][7]
     int32_t *scalars;        // [N][4]: reward (f32 bits), raw reward, current_time_step, flags << 8 | done
@@ -74,7 +91,7 @@ struct SmInst {
     int J, M, max_time_op, max_time_jobs, sum_op;
     float f_mto, f_mtj, f_sop, f_M;       // the divisors as floats ...
     float r_mto, r_mtj, r_sop, r_M;       // ... and their correctly rounded reciprocals
-    int pad_[3];
+    int Jcap, Mcap, block_words;          // state-block geometry of THIS instance: J, M rounded up to 4; 5*Jcap + Mcap + 12
 };
 struct JssLaunch {           // per-launch arguments
     int32_t tile_begin, tile_end;
@@ -82,6 +99,7 @@ struct JssLaunch {           // per-launch arguments
     int32_t rule, coin_mode, n_steps, write_obs;
     uint64_t seed, step_index;
     double cr_factor;        // CriticalRatio due_date_factor (dispatching.py:337-349); reference default 1.5
+    int32_t ticket_parity;   // mixed-batch step kernel: which of the two ticket counters this launch draws from
     const int32_t *actions;  // step
     int32_t *actions_out;    // policy
     const uint8_t *env_mask; // reset / import
