@@ -350,13 +350,18 @@ def main():
                     env_id_base=rank * N, seed=1234)
     J, M = env.jobs, env.machines
     env.reset()
-    if args.no_preroll:
-        acts = env.policy("RANDOM").clone()
-    else:
-        acts = preroll(env, "RANDOM", TA80_EPISODE if J * M >= 2000 else int(1.13 * J * M), torch)
+    # clocks are sampled from the pre-roll (the same kernels, ~0.5 s of load) through the timed region: the timed
+    # region alone (K launches of ~0.1 ms) is shorter than one nvidia-smi sampling period
     sampler = ClockSampler(local_rank)
     sampler.start()
+    if args.no_preroll:
+        acts = env.policy("RANDOM").clone()
+        for _ in range(3000):
+            *_, acts = env.step_sample(acts, "RANDOM")
+    else:
+        acts = preroll(env, "RANDOM", TA80_EPISODE if J * M >= 2000 else int(1.13 * J * M), torch)
     elapsed_ms, launches, acts = time_fused_steps(env, "RANDOM", acts, W, K, torch, dist, world)
+    torch.cuda.synchronize()
     clocks = sampler.stop()
     # the timed region is K launches of ONE kernel (the fused step), bracketed by CUDA events on the
     # launching stream: its average launch duration is elapsed / K (launch gaps, if any, count against us)
@@ -368,36 +373,50 @@ def main():
     e2e = None
     if not args.no_e2e:
         # pipelined host-buffer API: begin(step k) -> wait mask k -> host policy -> begin(step k+1) while the
-        # observation of step k is still crossing PCIe into its own pinned buffer -> consume obs k
-        mask = np.ascontiguousarray(env.action_mask.cpu().numpy())
-        env.host_step_begin(env.host_masked_random(mask, 0))
-        checksum = 0.0
+        # observation of step k is still crossing PCIe into its own pinned buffer -> consume obs k.
+        # packed: the observation crosses PCIe as 10-byte integer records per job and is expanded to the exact
+        # fp32 (N, J, 7) array by the host pool inside the timed region; plain: 28 bytes of fp32 per job by DMA.
+        bound = JssVecEnv.host_configure(0, local_rank)   # pool = usable CPUs / local ranks, on the GPU's NUMA node
+        threads = int(env._L.jss_host_threads())
 
-        def e2e_step(k):
-            m, rew, dn = env.host_wait_mask()
-            env.host_step_begin(env.host_masked_random(m, k))
-            return env.host_wait_obs(previous=True)      # the step's observation, on the host
+        def run_e2e(packed, steps):
+            mask = np.ascontiguousarray(env.action_mask.cpu().numpy())
+            env.host_step_begin(env.host_masked_random(mask, 0), packed=packed)
+            checksum = 0.0
 
-        for k in range(1, 4):
-            e2e_step(k)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for k in range(args.e2e_steps):
-            obs_host = e2e_step(10 + k)
-            checksum += float(obs_host[0, 0, 0])          # touch the result
-        env.host_wait_obs()
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * N * args.e2e_steps / float(dt.item()), "unit": UNIT,
+            def e2e_step(k):
+                m, rew, dn = env.host_wait_mask()
+                env.host_step_begin(env.host_masked_random(m, k), packed=packed)
+                return env.host_wait_obs(previous=True)      # the step's observation, fp32 on the host
+
+            for k in range(1, 4):
+                e2e_step(k)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for k in range(steps):
+                obs_host = e2e_step(10 + k)
+                checksum += float(obs_host[k % N, 0, 1])      # touch the result
+            env.host_wait_obs()
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return world * N * steps / float(dt.item())
+
+        ms_b, ws_b = int(env._b.mask_stride), int(env._L.jss_host_wire_stride(env._h))
+        v_packed = run_e2e(True, args.e2e_steps)
+        v_plain = run_e2e(False, max(10, args.e2e_steps // 4))
+        e2e = {"value": v_packed, "unit": UNIT,
                "h2d_bytes_per_step": 4 * N,
-               "d2h_bytes_per_step": N * int(env._b.mask_stride) + N * J * 7 * 4 + 16 * N,
-               "steps": args.e2e_steps,
-               "note": "jss_host_step_begin / jss_host_wait (pinned host buffers): H2D actions, step kernel, D2H mask + "
-                       "scalars + real_obs every step; host masked-random policy from the host mask; PCIe-bound"}
+               "d2h_bytes_per_step": N * ms_b + N * ws_b + 16 * N,
+               "steps": args.e2e_steps, "host_threads": threads, "numa_bound_cpus": bound,
+               "fp32_dma_variant": {"value": v_plain, "d2h_bytes_per_step": N * ms_b + N * J * 7 * 4 + 16 * N},
+               "note": "jss_host_step_begin_packed / jss_host_wait / jss_host_expand_obs (pinned host buffers): H2D actions, step "
+                       "kernel, D2H mask + scalar records + packed integer observation rows (10 B per job) every step, expansion "
+                       "to the exact fp32 (N, J, 7) observation by the host pool and the host masked-random policy inside the "
+                       "timed region; fp32_dma_variant = the same with 28 B per job of fp32 real_obs over PCIe"}
     env.close()
     del env
 

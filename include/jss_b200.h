@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define JSS_ABI_VERSION 1
+#define JSS_ABI_VERSION 2
 
 /* limits of the one-warp-per-env kernels */
 #define JSS_MAX_JOBS 128
@@ -214,6 +214,27 @@ int jss_step_host(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, flo
 int jss_host_step_begin(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, float *obs_host,
                         int32_t *scalars_host, void *after_stream);
 int jss_host_wait(jss_t *h, int what);
+
+/* Packed form of the pipelined host-buffer step: instead of the 28 bytes per job of fp32 real_obs, 10 bytes per job
+ * cross PCIe -- the INTEGER numerators of the observation columns (jss_env.py:102-111: legal bit,
+ * time_until_finish_current_op, todo_time_step, the stale column-4 numerator, idle_time_jobs_last_op,
+ * total_idle_time_jobs; column 3 is derivable) -- and jss_host_expand_obs() rebuilds the exact float observation
+ * on the host (multi-threaded; same correctly rounded quotients as the device real_obs, bit for bit).
+ * wire_host: [N][jss_host_wire_stride()] bytes (pinned).  scalars_host is required (the expansion reads
+ * current_time_step from it).  Waiting works as for jss_host_step_begin: JSS_WAIT_OBS* = the wire rows have landed. */
+int jss_host_step_begin_packed(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, uint8_t *wire_host,
+                               int32_t *scalars_host, void *after_stream);
+int64_t jss_host_wire_stride(jss_t *h);
+/* wire rows + scalar records of one step -> obs_host [N][J][7] fp32 (rows of env i: J_i * 7 floats written). */
+int jss_host_expand_obs(jss_t *h, const uint8_t *wire_host, const int32_t *scalars_host, float *obs_host);
+
+/* Host worker pool shared by jss_host_masked_random / jss_host_expand_obs: `threads` workers (0 = the CPUs this
+ * process may use, divided by LOCAL_WORLD_SIZE under torchrun); bind_numa_of_device >= 0 binds them (and the calling
+ * thread) to the CPUs of that GPU's NUMA node.  Returns the number of CPUs bound (0 = unbound).  Call before first use. */
+int jss_host_configure(int threads, int bind_numa_of_device);
+int jss_host_threads(void);
+/* Cap the SIMD level of jss_host_expand_obs: 0 scalar, 1 AVX2, 2 AVX-512 (default: best available).  For tests. */
+int jss_host_set_simd(int level);
 
 /* --- auxiliary ----------------------------------------------------------- */
 

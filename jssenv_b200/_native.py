@@ -13,7 +13,7 @@ import numpy as np
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libjss_b200.so")
 
-JSS_ABI_VERSION = 1
+JSS_ABI_VERSION = 2
 ACTION_SKIP, ACTION_ADVANCE = -1, -2
 CREATE_AUTO_RESET, CREATE_RECORD_SOLUTION = 1, 2
 FLAG_DONE, FLAG_ERROR, FLAG_NOOP_LEGAL = 1, 2, 4
@@ -27,7 +27,8 @@ EXPORTED_SYMBOLS = (
     "jss_abi_version", "jss_create", "jss_destroy", "jss_last_error", "jss_load_instances", "jss_assign",
     "jss_get_buffers", "jss_instance_scalars", "jss_reset", "jss_step", "jss_policy", "jss_rollout",
     "jss_step_host", "jss_host_step_begin", "jss_host_wait", "jss_step_sample", "jss_stats", "jss_export_state", "jss_import_state", "jss_host_masked_random",
-    "jss_launch_count", "jss_set_cr_due_date_factor",
+    "jss_launch_count", "jss_set_cr_due_date_factor", "jss_host_step_begin_packed", "jss_host_wire_stride",
+    "jss_host_expand_obs", "jss_host_configure", "jss_host_threads", "jss_host_set_simd",
 )
 
 
@@ -67,6 +68,18 @@ def _declare(L):
     L.jss_step_host.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.jss_host_step_begin.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.jss_host_wait.argtypes = [c_void_p, c_int]
+    L.jss_host_step_begin_packed.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.jss_host_step_begin_packed.restype = c_int
+    L.jss_host_wire_stride.argtypes = [c_void_p]
+    L.jss_host_wire_stride.restype = c_int64
+    L.jss_host_expand_obs.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    L.jss_host_expand_obs.restype = c_int
+    L.jss_host_configure.argtypes = [c_int, c_int]
+    L.jss_host_configure.restype = c_int
+    L.jss_host_set_simd.argtypes = [c_int]
+    L.jss_host_set_simd.restype = c_int
+    L.jss_host_threads.argtypes = []
+    L.jss_host_threads.restype = c_int
     L.jss_stats.argtypes = [c_void_p, POINTER(c_int64), c_void_p]
     L.jss_export_state.argtypes = [c_void_p, c_void_p]
     L.jss_import_state.argtypes = [c_void_p, c_void_p, c_void_p]

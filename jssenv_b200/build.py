@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(PKG, "csrc", "jss_api.cu")
+SRCS = [os.path.join(PKG, "csrc", "jss_api.cu"), os.path.join(PKG, "csrc", "jss_host.cpp")]
 OUT = os.path.join(PKG, "libjss_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     extra = os.environ.get("JSS_NVCC_EXTRA", "").split()   # experiments only (e.g. -DJSS_MIN_CTAS=4)
-    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRCS
     subprocess.check_call(cmd)
     return OUT
 

@@ -33,10 +33,12 @@ static cudaError_t jss_launch_pdl(void (*kern)(KArgs...), int grid, int block, s
 #include <cstdio>
 #include <cstring>
 #include <string>
-#include <thread>
+#include <sched.h>
+#include <cctype>
 #include <vector>
 
 #include "jss_device.cuh"
+#include "jss_host.h"
 
 namespace {
 
@@ -45,6 +47,7 @@ std::string g_create_error;
 struct HostInst {
     int J, M;
     int64_t max_time_op, max_time_jobs, sum_op;
+    std::vector<int32_t> len;      // jobs_length (host copy: the packed-observation expansion needs it)
 };
 
 }  // namespace
@@ -74,13 +77,14 @@ struct jss_handle {
     JssSmemLayout sl_norem{}, sl_rem{};
     int class_tile_begin[3] = {0, 0, 0}, class_tile_end[3] = {0, 0, 0};  // KJ = 1, 2, 4
     int step_grid[16] = {0};                        // resident-CTA grids of the step kernel variants (filled lazily)
-    int ticket_parity = 0;                          // mixed-batch step kernel: which ticket counter the next launch draws from
     bool use_pdl = true;
     std::vector<int32_t> env_inst;
 
     // host-buffer stepping
     int32_t *dev_actions = nullptr;
     float *obs_staging = nullptr;                  // pipelined mode: device copy the D2H engine reads from
+    uint8_t *wire[2] = {nullptr, nullptr};         // packed mode: two alternating device rows buffers [N][wire_stride]
+    int64_t wire_stride = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
     cudaEvent_t ev_mask = nullptr, ev_staged = nullptr, ev_obs[2] = {nullptr, nullptr};
     int pipe_cur = 0;                              // which ev_obs belongs to the latest begin
@@ -138,7 +142,7 @@ JssSmemLayout step_layout(jss_t *h, bool want_rem) {
     sl.statein_words = h->p.block_words;
     sl.off_len = (int32_t)sizeof(SmInst) + sl.ops_elems * 2;
     sl.off_rem = sl.off_len + sl.len_elems * 4;
-    sl.off_warp0 = sl.off_rem + sl.rem_elems * 2 + 16;       // 16 spare bytes: the mixed kernel's chunk ticket
+    sl.off_warp0 = sl.off_rem + sl.rem_elems * 2;
     sl.off_scratch = 16 + sl.statein_words * 4;
     sl.warp_stride = sl.off_scratch + sl.scratch_words * 4 + sl.statein_words * 4;   // + state-out staging
     return sl;
@@ -183,18 +187,16 @@ int launch_step_uniform(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStre
 template <int SAMPLE>
 int launch_step_mixed(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStream_t st) {
     JssLaunch a = a_in;
-    a.ticket_parity = h->ticket_parity;
     const JssSmemLayout sl = step_layout(h, want_rem);
     const size_t smem = (size_t)sl.off_warp0 + (size_t)JSS_WARPS_PER_CTA * sl.warp_stride;
     auto kern = jss_step_mixed_kernel<SAMPLE>;
     const int slot = 12 + SAMPLE + (want_rem ? 1 : 0);
     int rc = step_grid_for(h, kern, slot, smem);
     if (rc) return rc;
-    const int grid = std::max(1, std::min(h->p.n_chunks, h->step_grid[slot]));
+    const int grid = h->p.n_cta_ranges;                   // one static equal-cost range per CTA (all resident: SMs x 3)
     if (h->use_pdl) JSS_CUDA(h, JSS_LAUNCH_PDL(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl));
     else JSS_LAUNCH(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl);
     JSS_CUDA(h, cudaGetLastError());
-    h->ticket_parity ^= 1;
     h->launches += 1;
     return JSS_OK;
 }
@@ -348,7 +350,7 @@ int jss_load_instances(jss_t *h, int n_inst, const int32_t *jobs, const int32_t 
             return fail(h, JSS_ERR_UNSUPPORTED, "instance %d: %dx%d exceeds the %dx%d kernel limit", k, J, M,
                         JSS_MAX_JOBS, JSS_MAX_MACHINES);
         const int32_t *mm = machine + offsets[k], *dd = duration + offsets[k];
-        HostInst hi{J, M, 0, 0, 0};
+        HostInst hi{J, M, 0, 0, 0, std::vector<int32_t>((size_t)J)};
         JssInstDesc d{};
         d.J = J; d.M = M;
         d.ops_off = (int32_t)ops.size();
@@ -372,6 +374,7 @@ int jss_load_instances(jss_t *h, int n_inst, const int32_t *jobs, const int32_t 
                 hi.max_time_op = std::max<int64_t>(hi.max_time_op, t);  // jss_env.py:86
             }
             len[d.len_off + j] = (int32_t)total;                        // jss_env.py:87
+            hi.len[j] = (int32_t)total;
             hi.sum_op += total;                                         // jss_env.py:88
             hi.max_time_jobs = std::max(hi.max_time_jobs, total);       // jss_env.py:89
             int64_t suffix = 0;
@@ -486,24 +489,34 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
     if (off16 >= (1ull << 32)) return fail(h, JSS_ERR_UNSUPPORTED, "state exceeds 64 GiB");
     const size_t state_words = (size_t)off16 * 4;
 
-    // chunks for the mixed-batch step kernel: runs of consecutive tiles of one lane class with about equal cost,
-    // ~6 per resident CTA, so that drawing them by ticket balances the SMs whatever the instance mix is
-    std::vector<JssChunk> chunks;
+    // mixed-batch step kernel: one contiguous, equal-cost tile range per persistent CTA.  Cost of an env-step as a
+    // function of J, measured on uniform 65 536-env batches (profiles/r02_probe_shapes.json): 0.95 / 0.90 / 0.97 /
+    // 1.17 / 1.41 ns for J = 15 / 20 / 30 / 50 / 100 -- small envs are latency-bound, so the cost is far from
+    // proportional to the bytes they move.
+    std::vector<JssCtaRange> ranges;
     {
-        double total = 0;
-        for (double c : tile_cost) total += c;
-        const double target = total / std::max(1, h->sm_count * JSS_MIN_CTAS * 6);
-        for (int c = 2; c >= 0; c--) {
-            int t = h->class_tile_begin[c];
-            const int te = h->class_tile_end[c];
-            while (t < te) {
-                double acc = 0;
-                int e = t;
-                while (e < te && (e == t || acc + tile_cost[e] <= target)) acc += tile_cost[e++];
-                chunks.push_back(JssChunk{t, e, c == 0 ? 1 : (c == 1 ? 2 : 4), 0});
-                t = e;
-            }
+        double ca = 0.84, cb = 0.0057;
+        if (const char *e = getenv("JSS_COST_A")) ca = atof(e);
+        if (const char *e = getenv("JSS_COST_B")) cb = atof(e);
+        std::vector<double> cum(tiles.size() + 1, 0.0);
+        for (size_t t = 0; t < tiles.size(); t++) {
+            const int k = tiles[t].inst_count >> 8, cnt = tiles[t].inst_count & 255;
+            cum[t + 1] = cum[t] + cnt * (ca + cb * h->insts[k].J);
         }
+        const int n_cta = std::max(1, std::min((int)tiles.size(), h->sm_count * JSS_MIN_CTAS));
+        // tiles are ordered KJ=4 | KJ=2 | KJ=1; ends of the first two groups (empty classes collapse)
+        const int c4e = h->class_tile_end[2] > h->class_tile_begin[2] ? h->class_tile_end[2] : 0;
+        const int c2e = h->class_tile_end[1] > h->class_tile_begin[1] ? h->class_tile_end[1] : c4e;
+        int t = 0;
+        for (int b = 0; b < n_cta; b++) {
+            const double target = cum.back() * (b + 1) / n_cta;
+            int e = t;
+            while (e < (int)tiles.size() && (b == n_cta - 1 || cum[e + 1] <= target + 1e-9)) e++;
+            auto clampi = [&](int v) { return std::min(std::max(v, t), e); };
+            ranges.push_back(JssCtaRange{t, clampi(c4e), clampi(c2e), e});
+            t = e;
+        }
+        if (t != (int)tiles.size()) return fail(h, JSS_ERR_INVALID, "internal: CTA ranges do not cover the tile list");
     }
 
     JssParams &p = h->p;
@@ -535,26 +548,24 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
     int rc;
     int32_t *d_order = nullptr;
     JssTile *d_tiles = nullptr;
-    JssChunk *d_chunks = nullptr;
+    JssCtaRange *d_ranges = nullptr;
     uint32_t *d_soff = nullptr, *d_hoff = nullptr;
     if ((rc = dev_alloc(h, &d_order, (size_t)N))) return rc;
     if ((rc = dev_alloc(h, &d_tiles, tiles.size()))) return rc;
-    if ((rc = dev_alloc(h, &d_chunks, chunks.size()))) return rc;
+    if ((rc = dev_alloc(h, &d_ranges, ranges.size()))) return rc;
     if ((rc = dev_alloc(h, &d_soff, (size_t)N))) return rc;
     if ((rc = dev_alloc(h, &d_hoff, (size_t)N))) return rc;
-    if ((rc = dev_alloc(h, &p.ticket, (size_t)4))) return rc;       // zero-initialised
     JSS_CUDA(h, cudaMemcpy(d_order, order.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
     JSS_CUDA(h, cudaMemcpy(d_tiles, tiles.data(), tiles.size() * sizeof(JssTile), cudaMemcpyHostToDevice));
-    JSS_CUDA(h, cudaMemcpy(d_chunks, chunks.data(), chunks.size() * sizeof(JssChunk), cudaMemcpyHostToDevice));
+    JSS_CUDA(h, cudaMemcpy(d_ranges, ranges.data(), ranges.size() * sizeof(JssCtaRange), cudaMemcpyHostToDevice));
     JSS_CUDA(h, cudaMemcpy(d_soff, state_off16.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
     JSS_CUDA(h, cudaMemcpy(d_hoff, hdr_off16.data(), (size_t)N * 4, cudaMemcpyHostToDevice));
     p.order = d_order;
     p.tiles = d_tiles;
-    p.chunks = d_chunks;
-    p.n_chunks = (int32_t)chunks.size();
+    p.cta_ranges = d_ranges;
+    p.n_cta_ranges = (int32_t)ranges.size();
     p.state_off16 = d_soff;
     p.hdr_off16 = d_hoff;
-    h->ticket_parity = 0;
     const size_t NJ = (size_t)N * jmax, NM = (size_t)N * mmax;
     if ((rc = dev_alloc(h, &p.state, state_words))) return rc;
     if ((rc = dev_alloc(h, &p.mask, (size_t)N * p.mask_stride))) return rc;
@@ -685,15 +696,15 @@ int jss_step_host(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, flo
     return JSS_OK;
 }
 
-int jss_host_step_begin(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, float *obs_host,
-                        int32_t *scalars_host, void *after_stream) {
+namespace {
+int host_step_begin_impl(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, float *obs_host, uint8_t *wire_host,
+                         int32_t *scalars_host, void *after_stream) {
     int rc = check_ready(h);
     if (rc) return rc;
     if (!actions_host) return fail(h, JSS_ERR_INVALID, "jss_host_step_begin: actions_host is NULL");
     const JssParams &p = h->p;
     const size_t N = (size_t)p.n_envs, obs_bytes = N * p.jobs_max * 7 * 4;
     if (!h->pipe_ready) {
-        if ((rc = dev_alloc(h, &h->obs_staging, N * p.jobs_max * 7, false))) return rc;
         JSS_CUDA(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
         JSS_CUDA(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
         JSS_CUDA(h, cudaEventCreateWithFlags(&h->ev_mask, cudaEventDisableTiming));
@@ -703,6 +714,13 @@ int jss_host_step_begin(jss_t *h, const int32_t *actions_host, uint8_t *mask_hos
             JSS_CUDA(h, cudaEventRecord(h->ev_obs[k], h->s_copy));
         }
         h->pipe_ready = true;
+    }
+    if (obs_host && !h->obs_staging && (rc = dev_alloc(h, &h->obs_staging, N * p.jobs_max * 7, false))) return rc;
+    if (wire_host && !h->wire[0]) {
+        // 16-byte multiple with >= 6 bytes of slack behind the last record (the host expansion loads 16 bytes per job)
+        h->wire_stride = round_up(JSS_WIRE_JOB_BYTES * p.jobs_max + 6, 16);
+        for (int k = 0; k < 2; k++)
+            if ((rc = dev_alloc(h, &h->wire[k], N * (size_t)h->wire_stride))) return rc;
     }
     cudaStream_t sc = h->s_compute;
     // order the pipeline after whatever the caller enqueued on its own stream (reset, device-side steps ...)
@@ -737,13 +755,102 @@ int jss_host_step_begin(jss_t *h, const int32_t *actions_host, uint8_t *mask_hos
         // 2.9 KB/env PCIe transfer on its own stream, overlapping the host policy and the next launch
         JSS_CUDA(h, cudaStreamWaitEvent(sc, h->ev_obs[prev], 0));      // previous D2H has drained the staging copy
         JSS_CUDA(h, cudaMemcpyAsync(h->obs_staging, p.obs, obs_bytes, cudaMemcpyDeviceToDevice, sc));
-        JSS_CUDA(h, cudaEventRecord(h->ev_staged, sc));
-        JSS_CUDA(h, cudaStreamWaitEvent(h->s_copy, h->ev_staged, 0));
-        JSS_CUDA(h, cudaMemcpyAsync(obs_host, h->obs_staging, obs_bytes, cudaMemcpyDeviceToHost, h->s_copy));
+    } else if (wire_host) {
+        // packed rows: 10 bytes per job instead of 28; two device buffers alternate, so this pack only has to wait
+        // for the D2H that read the same buffer two begins ago
+        JSS_CUDA(h, cudaStreamWaitEvent(sc, h->ev_obs[h->pipe_cur], 0));
+        JssLaunch a{};
+        a.mode = JSS_MODE_PACK;
+        a.wire = h->wire[h->pipe_cur];
+        a.wire_stride = (int32_t)h->wire_stride;
+        if ((rc = launch_all(h, a, false, sc))) return rc;
     }
+    // the copy stream never runs ahead of the step (also when nothing large is copied: JSS_WAIT_OBS is the barrier
+    // callers take before going back to the stream-ordered entry points)
+    JSS_CUDA(h, cudaEventRecord(h->ev_staged, sc));
+    JSS_CUDA(h, cudaStreamWaitEvent(h->s_copy, h->ev_staged, 0));
+    if (obs_host)
+        JSS_CUDA(h, cudaMemcpyAsync(obs_host, h->obs_staging, obs_bytes, cudaMemcpyDeviceToHost, h->s_copy));
+    else if (wire_host)
+        JSS_CUDA(h, cudaMemcpyAsync(wire_host, h->wire[h->pipe_cur], N * (size_t)h->wire_stride, cudaMemcpyDeviceToHost,
+                                    h->s_copy));
     JSS_CUDA(h, cudaEventRecord(h->ev_obs[h->pipe_cur], h->s_copy));
     return JSS_OK;
 }
+}  // namespace
+
+int jss_host_step_begin(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, float *obs_host,
+                        int32_t *scalars_host, void *after_stream) {
+    return host_step_begin_impl(h, actions_host, mask_host, obs_host, nullptr, scalars_host, after_stream);
+}
+
+int jss_host_step_begin_packed(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, uint8_t *wire_host,
+                               int32_t *scalars_host, void *after_stream) {
+    if (!wire_host || !scalars_host)
+        return fail(h, JSS_ERR_INVALID, "jss_host_step_begin_packed: wire_host and scalars_host are required");
+    return host_step_begin_impl(h, actions_host, mask_host, nullptr, wire_host, scalars_host, after_stream);
+}
+
+int64_t jss_host_wire_stride(jss_t *h) {
+    if (!h || !h->assigned) return JSS_ERR_STATE;
+    return round_up(JSS_WIRE_JOB_BYTES * h->p.jobs_max + 6, 16);
+}
+
+int jss_host_expand_obs(jss_t *h, const uint8_t *wire_host, const int32_t *scalars_host, float *obs_host) {
+    if (!h || !h->assigned) return fail(h, JSS_ERR_STATE, "jss_host_expand_obs: jss_assign must be called first");
+    if (!wire_host || !scalars_host || !obs_host) return fail(h, JSS_ERR_INVALID, "jss_host_expand_obs: NULL buffer");
+    std::vector<JssHostInst> hi(h->insts.size());
+    for (size_t k = 0; k < h->insts.size(); k++)
+        hi[k] = JssHostInst{h->insts[k].J, h->insts[k].M, h->insts[k].max_time_op, h->insts[k].max_time_jobs,
+                            h->insts[k].sum_op, h->insts[k].len.data()};
+    JssHostExpandArgs a{wire_host, jss_host_wire_stride(h), scalars_host, h->env_inst.data(), hi.data(), obs_host,
+                        h->p.jobs_max, 0, h->n_envs};
+    jss_host_expand_impl(&a);
+    return JSS_OK;
+}
+
+int jss_host_configure(int threads, int bind_numa_of_device) {
+    std::vector<int> cpus;
+#ifndef JSS_EMU
+    if (bind_numa_of_device >= 0) {
+        // CPUs of the NUMA node the GPU hangs off (pinned buffers and the expansion threads stay local to it)
+        char bus[32] = {0};
+        if (cudaDeviceGetPCIBusId(bus, sizeof bus, bind_numa_of_device) == cudaSuccess) {
+            for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+            char path[160];
+            snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+            int node = -1;
+            if (FILE *f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+            if (node >= 0) {
+                snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+                if (FILE *f = fopen(path, "r")) {
+                    int a = 0, b = 0;
+                    char sep = 0;
+                    cpu_set_t allowed;
+                    const bool have = sched_getaffinity(0, sizeof allowed, &allowed) == 0;
+                    while (fscanf(f, "%d", &a) == 1) {
+                        b = a;
+                        if (fscanf(f, "%c", &sep) == 1 && sep == '-') { if (fscanf(f, "%d", &b) != 1) b = a; if (fscanf(f, "%c", &sep) != 1) sep = 0; }
+                        for (int c = a; c <= b; c++)
+                            if (!have || CPU_ISSET(c, &allowed)) cpus.push_back(c);
+                        if (sep != ',') break;
+                    }
+                    fclose(f);
+                }
+            }
+        }
+        (void)cudaGetLastError();
+    }
+#else
+    (void)bind_numa_of_device;
+#endif
+    jss_host_pool_configure(threads, cpus.data(), (int)cpus.size());
+    return (int)cpus.size();
+}
+
+int jss_host_threads(void) { return jss_host_pool_size(); }
+
+int jss_host_set_simd(int level) { jss_host_simd_cap(level); return JSS_OK; }
 
 int jss_host_wait(jss_t *h, int what) {
     int rc = check_ready(h);
@@ -796,32 +903,7 @@ int jss_import_state(jss_t *h, const uint8_t *env_mask_dev, void *stream) {
 int jss_host_masked_random(const uint8_t *mask_host, int n, int width, int64_t row_stride, uint64_t seed,
                            uint64_t env_id_base, uint64_t step_index, int32_t *actions_host) {
     if (!mask_host || !actions_host || n < 0 || width <= 0 || row_stride < width) return JSS_ERR_INVALID;
-    auto work = [&](int lo, int hi) {
-        for (int e = lo; e < hi; e++) {
-            const uint8_t *row = mask_host + (size_t)e * (size_t)row_stride;
-            int cnt = 0;
-            for (int i = 0; i < width; i++) cnt += row[i] != 0;
-            int act = JSS_ACTION_SKIP;
-            if (cnt > 0) {
-                uint32_t r = jss_pick(jss_hash3(seed, env_id_base + (uint64_t)e, step_index), (uint32_t)cnt);
-                for (int i = 0; i < width; i++)
-                    if (row[i]) { if (r == 0) { act = i; break; } r--; }
-            }
-            actions_host[e] = act;
-        }
-    };
-    size_t cpus = std::max(1u, std::thread::hardware_concurrency());
-    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {          // container CPU quota, if any
-        long long q = 0, per = 0;
-        if (fscanf(f, "%lld %lld", &q, &per) == 2 && q > 0 && per > 0) cpus = std::min<size_t>(cpus, (size_t)((q + per - 1) / per));
-        fclose(f);
-    }
-    const int nthreads = (int)std::min<size_t>(cpus, std::max<size_t>(1, (size_t)n * width / (1 << 18)));
-    if (nthreads <= 1) { work(0, n); return JSS_OK; }
-    std::vector<std::thread> pool;
-    const int chunk = (n + nthreads - 1) / nthreads;
-    for (int t = 0; t < nthreads; t++) pool.emplace_back(work, std::min(n, t * chunk), std::min(n, (t + 1) * chunk));
-    for (auto &th : pool) th.join();
+    jss_host_masked_random_impl(mask_host, n, width, row_stride, seed, env_id_base, step_index, actions_host);   // persistent pool
     return JSS_OK;
 }
 

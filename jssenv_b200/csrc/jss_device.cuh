@@ -750,6 +750,33 @@ JSS_DEV void env_import(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, 
     env_derive_ops<KJ>(iv, s, lane);
 }
 
+// ---- packed observation row (host-buffer path) ---------------------------------------------------------
+// 10 bytes per job: w0 = legal | tufco << 1 | todo << 12 | col4 << 18, then idle_last and total_idle as 24-bit
+// little-endian integers (the makespan bound J*M*2047 < 2^24).  Column 3 (total_perform) is derivable on the host
+// from total_idle, todo, t and jobs_length.  jss_host_expand_obs() turns a row back into the exact real_obs floats.
+template <int KJ>
+JSS_DEV void env_pack(const JssLaunch &a, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane, float *scratch) {
+    uint16_t *st = reinterpret_cast<uint16_t *>(scratch);
+    if (KJ * lane < iv.si->J) {
+#pragma unroll
+        for (int i = 0; i < KJ; i++) {
+            const uint32_t w0 = ((s.lb >> i) & 1u) | ((uint32_t)s.tufco[i] << 1) | ((uint32_t)s.todo[i] << 12) |
+                                ((uint32_t)s.col4[i] << 18);
+            const uint32_t il = (uint32_t)s.idle_last[i], ti = (uint32_t)s.total_idle[i];
+            uint16_t *r = st + 5 * (KJ * lane + i);
+            r[0] = (uint16_t)w0; r[1] = (uint16_t)(w0 >> 16);
+            r[2] = (uint16_t)il;                                      // bytes 4,5
+            r[3] = (uint16_t)(((il >> 16) & 255u) | ((ti & 255u) << 8));   // byte 6 = idle[23:16], byte 7 = total[7:0]
+            r[4] = (uint16_t)(ti >> 8);                               // bytes 8,9
+        }
+    }
+    __syncwarp();
+    uint4 *dst = reinterpret_cast<uint4 *>(a.wire + (size_t)env * a.wire_stride);
+    const int n16 = (iv.si->J * 10 + 15) >> 4;
+    for (int k = lane; k < n16; k += 32) dst[k] = reinterpret_cast<const uint4 *>(scratch)[k];
+    __syncwarp();
+}
+
 // ---- CTA-level driver -----------------------------------------------------------------------
 struct JssSmemLayout {      // element counts; every region starts 16-byte aligned
     int32_t ops_elems, len_elems, rem_elems, scratch_words;
@@ -833,6 +860,7 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
     if (mode == JSS_MODE_POLICY) env_load_for_policy<KJ>(p, iv, env, lane, s, a.rule);
     else env_load<KJ>(p, iv, env, lane, s);
     if (mode == JSS_MODE_EXPORT) { env_export<KJ>(p, iv, s, env, lane); return; }
+    if (mode == JSS_MODE_PACK) { env_pack<KJ>(a, iv, s, env, lane, scratch); return; }
     if (mode == JSS_MODE_POLICY) {
         const uint32_t h = jss_hash3(a.seed, genv, a.step_index);
         const int act = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
@@ -1092,11 +1120,12 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     if (lane == 0) jss_bulk_store_wait_all();            // shared memory must outlive the bulk reads
 }
 
-// Mixed batch: ONE persistent launch covers the three lane classes.  The host cuts the (class, instance)-sorted
-// tile list into chunks of roughly equal cost, most expensive class first; CTAs draw chunks by ticket (longest
-// processing time first), so a 15-job env costs what a 15-job env costs and the tail is filled with cheap work.
-// Launch k draws from ticket[k & 1] and zeroes ticket[(k + 1) & 1] for its successor (which cannot start
-// drawing before this grid has completed: jss_pdl_wait).
+// Mixed batch: ONE persistent launch covers the three lane classes.  The host splits the (class, instance)-sorted
+// tile list into one contiguous, equal-COST range per CTA (per-class costs measured on uniform batches, see
+// jss_assign); a CTA walks its range class by class -- three complete loops in sequence, so each lane class keeps the
+// register allocation of its stand-alone kernel -- and re-stages instance tables only when the instance changes.
+// Co-resident CTAs work on different classes, which mixes issue-bound (100-job) and latency-bound (15-job) warps
+// on every SM.
 template <int SAMPLE>
 __global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, JSS_MIN_CTAS)
 jss_step_mixed_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
@@ -1109,29 +1138,17 @@ jss_step_mixed_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     JssWarpSmem w;
     jss_step_carve(sl, sm, warp, w);
-    int *s_chunk = reinterpret_cast<int *>(sm + sl.off_warp0 - 16);     // 16 spare bytes in front of the warp regions
     if (lane == 0) jss_mbar_init(w.mbar);
     InstView iv;
     iv.ops = sm_ops; iv.len = sm_len; iv.rem = sm_rem; iv.si = si;
     jss_pdl_launch_dependents();
+    const int4 r = *reinterpret_cast<const int4 *>(p.cta_ranges + blockIdx.x);   // tile cuts: [x,y) KJ=4, [y,z) KJ=2, [z,w) KJ=1
     jss_pdl_wait();
-    if (blockIdx.x == 0 && threadIdx.x == 0) p.ticket[a.ticket_parity ^ 1] = 0u;
     int staged = -1;
     uint32_t phase = 0;
-    for (;;) {
-        __syncthreads();                                 // all warps are done with the previous chunk
-        if (threadIdx.x == 0) *s_chunk = (int)atomicAdd(&p.ticket[a.ticket_parity], 1u);
-        __syncthreads();
-        const int c = *s_chunk;
-        if (c >= p.n_chunks) break;
-        const int4 ch = *reinterpret_cast<const int4 *>(p.chunks + c);   // JssChunk
-        if (ch.z == 4)
-            jss_step_tiles<4, SAMPLE, false>(p, a, sl, iv, si, sm_ops, sm_len, sm_rem, w, warp, lane, ch.x, ch.y, 1, staged, phase);
-        else if (ch.z == 2)
-            jss_step_tiles<2, SAMPLE, false>(p, a, sl, iv, si, sm_ops, sm_len, sm_rem, w, warp, lane, ch.x, ch.y, 1, staged, phase);
-        else
-            jss_step_tiles<1, SAMPLE, false>(p, a, sl, iv, si, sm_ops, sm_len, sm_rem, w, warp, lane, ch.x, ch.y, 1, staged, phase);
-    }
+    jss_step_tiles<4, SAMPLE, false>(p, a, sl, iv, si, sm_ops, sm_len, sm_rem, w, warp, lane, r.x, r.y, 1, staged, phase);
+    jss_step_tiles<2, SAMPLE, false>(p, a, sl, iv, si, sm_ops, sm_len, sm_rem, w, warp, lane, r.y, r.z, 1, staged, phase);
+    jss_step_tiles<1, SAMPLE, false>(p, a, sl, iv, si, sm_ops, sm_len, sm_rem, w, warp, lane, r.z, r.w, 1, staged, phase);
     if (lane == 0) jss_bulk_store_wait_all();            // shared memory must outlive the bulk reads
 }
 

@@ -7,7 +7,7 @@
 #pragma once
 #include <stdint.h>
 
-#if defined(__CUDACC__) || defined(JSS_EMU)
+#if defined(__CUDACC__)
 #define JSS_HD __host__ __device__
 #else
 #define JSS_HD

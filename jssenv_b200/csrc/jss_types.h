@@ -48,10 +48,8 @@ struct JssTile {       // one CTA work item: up to `count` envs of ONE instance 
     uint32_t block16;  // block size of this tile's instance in 16-byte units
 };
 
-struct JssChunk {      // mixed batches: a run of consecutive tiles of ONE lane class, handed out by ticket
-    int32_t tile_begin, tile_end;
-    int32_t kj;        // 1, 2 or 4 jobs per lane
-    int32_t pad_;
+struct JssCtaRange {   // mixed batches: the tiles of one persistent CTA, cut at the lane-class boundaries
+    int32_t t4, t2, t1, tend;   // [t4, t2) KJ = 4 tiles, [t2, t1) KJ = 2, [t1, tend) KJ = 1
 };
 
 struct JssParams {
@@ -65,9 +63,8 @@ struct JssParams {
     const uint16_t *rem_pool;
     const int32_t *order;    // env ids grouped by (KJ class, instance)
     const JssTile *tiles;
-    const JssChunk *chunks;  // mixed-batch step kernel: work list, most expensive lane class first
-    int32_t n_chunks;
-    uint32_t *ticket;        // [2] chunk tickets; launch k draws from ticket[k & 1] and zeroes ticket[(k + 1) & 1]
+    const JssCtaRange *cta_ranges;   // mixed-batch step kernel: one equal-cost contiguous tile range per CTA
+    int32_t n_cta_ranges;
     const uint32_t *state_off16;   // per env: start of its state block, in 16-byte units (tile order, see JssTile)
     const uint32_t *hdr_off16;     // per env: start of its 4-word header (t, flags, episode steps / return), 16-byte units
     int32_t *state;          // per-env blocks of 5 * Jcap_i + Mcap_i + 12 words (Jcap_i, Mcap_i: the env's instance)
@@ -99,10 +96,11 @@ struct JssLaunch {           // per-launch arguments
     int32_t rule, coin_mode, n_steps, write_obs;
     uint64_t seed, step_index;
     double cr_factor;        // CriticalRatio due_date_factor (dispatching.py:337-349); reference default 1.5
-    int32_t ticket_parity;   // mixed-batch step kernel: which of the two ticket counters this launch draws from
     const int32_t *actions;  // step
     int32_t *actions_out;    // policy
     const uint8_t *env_mask; // reset / import
+    uint8_t *wire;           // pack: [N][wire_stride] packed observation rows (JSS_WIRE_JOB_BYTES per job)
+    int32_t wire_stride;
     SmInst uni;              // scalars of the single instance of a uniform batch (step kernel, UNI = true)
 };
 
@@ -112,6 +110,7 @@ struct JssLaunch {           // per-launch arguments
 #define JSS_MODE_POLICY 3
 #define JSS_MODE_EXPORT 4
 #define JSS_MODE_IMPORT 5
+#define JSS_MODE_PACK 6     // packed observation wire rows for the host-buffer path (jss_host_step_begin_packed)
 
 #ifndef JSS_WARPS_PER_CTA
 #define JSS_WARPS_PER_CTA 8

@@ -212,9 +212,11 @@ class JssVecEnv:
         return obs, hv["reward"], hv["done"], np.zeros(n, np.bool_), {}
 
     # pipelined form: begin -> wait_mask -> (choose next actions) -> begin ... ; obs lands in alternating buffers
-    def host_step_begin(self, actions: np.ndarray):
+    def host_step_begin(self, actions: np.ndarray, packed: bool = False):
         """Enqueue one host-buffer step and return immediately (see jss_host_step_begin).  Results land
-        in this call's slot of two alternating pinned buffer sets; use host_wait_mask()/host_wait_obs()."""
+        in this call's slot of two alternating pinned buffer sets; use host_wait_mask()/host_wait_obs().
+        packed=True ships the observation as 10-byte integer records per job instead of 28 bytes of fp32
+        (jss_host_step_begin_packed); host_wait_obs() then expands them to the exact float observation."""
         a = np.ascontiguousarray(actions, dtype=np.int32)
         n, J = self.num_envs, self.jobs
         if not hasattr(self, "_pipe"):
@@ -222,16 +224,39 @@ class JssVecEnv:
             pin = N.backend.name == "cuda"
             mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin)   # noqa: E731
             ms = int(self._b.mask_stride)
-            self._pipe = [{"mask": mk((n, ms), torch.uint8), "obs": mk((n, J, 7), torch.float32),
-                           "scalars": mk((n, 4), torch.int32), "actions": mk((n,), torch.int32)} for _ in range(2)]
+            ws = int(self._L.jss_host_wire_stride(self._h))
+            self._pipe = [{"mask": mk((n, ms), torch.uint8), "obs": None, "wire": None, "wire_stride": ws,
+                           "scalars": mk((n, 4), torch.int32), "actions": mk((n,), torch.int32), "packed": False,
+                           "expanded": True} for _ in range(2)]
             self._pipe_slot = 0
+            self._pipe_mk = mk
+            self._pipe_inflight = 0
+        if self._pipe_inflight >= 2:
+            # the slot about to be reused belongs to the begin before the latest one: its transfers must have drained
+            N.check(self._h, self._L.jss_host_wait(self._h, N.WAIT_OBS_PREV), "jss_host_wait")
         self._pipe_slot ^= 1
         b = self._pipe[self._pipe_slot]
+        if b["obs"] is None:
+            import torch
+            # fp32 observation buffer: DMA target (pinned) in plain mode, expansion target in packed mode
+            b["obs"] = self._pipe_mk((n, J, 7), torch.float32)
+        if packed and b["wire"] is None:
+            import torch
+            b["wire"] = self._pipe_mk((n, b["wire_stride"]), torch.uint8)
         b["actions"].numpy()[:] = a                      # pinned copy: the H2D must not race with the caller's array
-        rc = self._L.jss_host_step_begin(self._h, ctypes.c_void_p(b["actions"].data_ptr()),
-                                         ctypes.c_void_p(b["mask"].data_ptr()), ctypes.c_void_p(b["obs"].data_ptr()),
-                                         ctypes.c_void_p(b["scalars"].data_ptr()), self._stream())
+        b["packed"] = bool(packed)
+        b["expanded"] = not packed
+        if packed:
+            rc = self._L.jss_host_step_begin_packed(self._h, ctypes.c_void_p(b["actions"].data_ptr()),
+                                                    ctypes.c_void_p(b["mask"].data_ptr()),
+                                                    ctypes.c_void_p(b["wire"].data_ptr()),
+                                                    ctypes.c_void_p(b["scalars"].data_ptr()), self._stream())
+        else:
+            rc = self._L.jss_host_step_begin(self._h, ctypes.c_void_p(b["actions"].data_ptr()),
+                                             ctypes.c_void_p(b["mask"].data_ptr()), ctypes.c_void_p(b["obs"].data_ptr()),
+                                             ctypes.c_void_p(b["scalars"].data_ptr()), self._stream())
         N.check(self._h, rc, "jss_host_step_begin")
+        self._pipe_inflight = min(2, self._pipe_inflight + 1)
         return self._pipe_slot
 
     def host_wait_mask(self):
@@ -244,9 +269,21 @@ class JssVecEnv:
 
     def host_wait_obs(self, previous: bool = False):
         """Block until the observation of the latest host_step_begin (or, with previous=True, of the one
-        before it, which may be consumed while the latest is still streaming) has landed; returns (N, J, 7)."""
+        before it, which may be consumed while the latest is still streaming) has landed; returns (N, J, 7)
+        float32.  In packed mode the integer rows are expanded here (multi-threaded host helper)."""
         N.check(self._h, self._L.jss_host_wait(self._h, N.WAIT_OBS_PREV if previous else N.WAIT_OBS), "jss_host_wait")
-        return self._pipe[self._pipe_slot ^ (1 if previous else 0)]["obs"].numpy()
+        b = self._pipe[self._pipe_slot ^ (1 if previous else 0)]
+        if b["packed"] and not b["expanded"]:
+            rc = self._L.jss_host_expand_obs(self._h, ctypes.c_void_p(b["wire"].data_ptr()),
+                                             ctypes.c_void_p(b["scalars"].data_ptr()), ctypes.c_void_p(b["obs"].data_ptr()))
+            N.check(self._h, rc, "jss_host_expand_obs")
+            b["expanded"] = True
+        return b["obs"].numpy()
+
+    @staticmethod
+    def host_configure(threads: int = 0, bind_numa_of_device: int = -1) -> int:
+        """Size / bind the host worker pool (jss_host_configure); call before the first host helper runs."""
+        return int(N.backend.library().jss_host_configure(int(threads), int(bind_numa_of_device)))
 
     def host_masked_random(self, mask: np.ndarray, step_index: int) -> np.ndarray:
         """Same draw as policy('RANDOM') but from a host mask (for host-side agents / tests)."""

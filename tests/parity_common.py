@@ -459,6 +459,39 @@ def check_host_pipeline(make_env, name, seed):
     return env
 
 
+def check_host_pipeline_packed(make_env, names, seed, n_steps=80):
+    """Packed host-buffer path: 10-byte integer rows over the wire + host expansion == device real_obs BIT FOR BIT
+    (and mask / reward / done as in the plain path), on a mixed batch, through done/auto-reset transitions."""
+    uniq = sorted(set(names))
+    cfg = {"instance_paths": uniq, "env_to_instance": [uniq.index(n) for n in names]}
+    env = make_env(len(names), cfg, seed=seed, auto_reset=True)
+    ref = make_env(len(names), cfg, seed=seed, auto_reset=True)
+    env.reset(); ref.reset()
+    # get past the trivial all-zero start: a few hundred device steps on both
+    for k in range(120):
+        a0 = ref.policy("RANDOM", step_index=k)
+        ref.step(a0); env.step(_np(a0))
+    mask = np.ascontiguousarray(_np(env.action_mask))
+    a = env.host_masked_random(mask, 1000)
+    env.host_step_begin(a, packed=True)
+    for k in range(1, n_steps):
+        mask, rew, done = env.host_wait_mask()
+        ref.step(a)
+        assert np.array_equal(mask, _np(ref.action_mask)), k
+        assert np.array_equal(rew, _np(ref.reward)) and np.array_equal(done, _np(ref.done))
+        nxt = env.host_masked_random(mask, 1000 + k)
+        expected = _np(ref.real_obs).copy()
+        env.host_step_begin(nxt, packed=True)          # next step enqueued while the previous rows may still stream
+        env._L.jss_host_set_simd(k % 3)                # scalar / AVX2 / AVX-512 expansion paths in turn
+        got = env.host_wait_obs(previous=True)
+        for i, J in enumerate(env.env_jobs):
+            assert np.array_equal(got[i, :J].view(np.uint32), expected[i, :J].view(np.uint32)), (k, i)
+        a = nxt
+    env._L.jss_host_set_simd(2)
+    env.host_wait_obs()
+    return env
+
+
 def synthetic_instance(J, M, seed, max_dur=99, permutation=True):
     """Random instance; with permutation=False a job may visit a machine several times / skip others
     (the reference accepts that: it only requires M (machine, duration) pairs per job)."""
@@ -616,10 +649,11 @@ def check_shard_invariance(make_env, n_total=24, n_steps=350, seed=77):
     names = ["ta01", "ta31", "ta51", "ta80"]
     e2i = np.arange(n_total) % len(names)
     for rule in ("RANDOM", "FIFO"):
-        whole = make_env(n_total, {"instance_paths": names, "env_to_instance": e2i}, seed=seed, auto_reset=True)
         cuts = [0, n_total // 2, n_total]
         cuts3 = [0, 5, 5 + 9, n_total]
         for cut in (cuts, cuts3):
+            # fresh envs per split: episode_count / last_makespan are cumulative statistics that reset() keeps
+            whole = make_env(n_total, {"instance_paths": names, "env_to_instance": e2i}, seed=seed, auto_reset=True)
             shards = [make_env(hi - lo, {"instance_paths": names, "env_to_instance": e2i[lo:hi]}, seed=seed,
                                auto_reset=True, env_id_base=lo) for lo, hi in zip(cut[:-1], cut[1:])]
             whole.reset(); whole._step_index = 0
@@ -642,4 +676,4 @@ def check_shard_invariance(make_env, n_total=24, n_steps=350, seed=77):
             assert comb == {**whole.stats(), "min_makespan": comb["min_makespan"]} or comb == whole.stats()
             for s in shards:
                 s.close()
-        whole.close()
+            whole.close()

@@ -144,3 +144,8 @@ def test_emu_tiny_uniform_batches():
 
 def test_emu_shard_invariance():
     pc.check_shard_invariance(make_env, n_steps=150)
+
+
+def test_emu_host_pipeline_packed():
+    pc.check_host_pipeline_packed(make_env, ["ta01", "ta31", "ta51", "ta80", "dmu16"], seed=5)
+    pc.check_host_pipeline_packed(make_env, ["ta80"] * 3, seed=6)

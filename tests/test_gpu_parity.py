@@ -276,3 +276,8 @@ def test_gpu_tiny_uniform_batches():
 
 def test_gpu_shard_invariance():
     pc.check_shard_invariance(make_env, n_total=48, n_steps=2400)
+
+
+def test_gpu_host_pipeline_packed():
+    pc.check_host_pipeline_packed(make_env, ["ta01", "ta11", "ta31", "ta51", "ta62", "ta80", "dmu16"] * 9, seed=5, n_steps=600)
+    pc.check_host_pipeline_packed(make_env, ["ta80"] * 3, seed=6)
