@@ -210,6 +210,34 @@ def python_reference_leg(instance, seconds, procs=None):
                       f"{instance}, masked-random policy, resets included: {sum(o['steps'] for o in outs)} steps, wall {wall:.1f} s"}
 
 
+def facade_latency(instance, seconds, device):
+    """us per JssEnv.step() through the single-env drop-in facade (one launch + one sync per transition; the
+    attributes are numpy reads of a pinned host block), README.md:43-65 loop with the masked-random policy."""
+    import numpy as np
+    from jssenv_b200 import JssEnv
+    env = JssEnv({"instance_path": instance}, device=device)
+    rng = np.random.default_rng(0)
+    obs = env.reset()
+    clock = time.perf_counter
+    steps, t_step = 0, 0.0
+    t_end = clock() + seconds
+    warm = 200
+    while clock() < t_end:
+        legal = np.flatnonzero(obs["action_mask"])
+        a = int(legal[rng.integers(len(legal))])
+        t0 = clock()
+        obs, _, done, _, _ = env.step(a)
+        dt = clock() - t0
+        if warm > 0:
+            warm -= 1
+        else:
+            t_step += dt; steps += 1
+        if done:
+            obs = env.reset()
+    env.close()
+    return t_step / max(1, steps) * 1e6, steps
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path on all usable host threads.  value = the C oracle port (the
     stronger baseline: ~75x faster per core than the Python original); the unmodified Python reference timed on the
@@ -425,6 +453,18 @@ def main():
     if args.configs == "all":
         KC = args.config_steps or max(K, 300)
         if world == 1:
+            # cfg1: ta01 single env through the drop-in facade (the GPU path; there is no CPU product path): latency per
+            # step() next to the unmodified Python reference's step() on the same box
+            fac = {}
+            for inst in ("ta01", "ta80"):
+                us, n_st = facade_latency(inst, 1.5, local_rank)
+                ref = python_reference_leg(inst, 2.0, procs=1) if not args.no_cpu else {"unavailable": "--no-cpu"}
+                fac[inst] = {"facade_us_per_step": us, "steps": n_st,
+                             "python_reference_us_per_step": ref.get("step_only_us"), "python_reference": ref.get("unavailable")}
+            configs["cfg1_single_env_facade"] = {
+                "workload": "JssEnv(env_config).step(a) one env at a time (gym.make('jss-v1') drop-in), masked-random policy: one fused "
+                            "step+decode launch and one stream sync per transition, outputs written by the GPU straight into pinned host memory",
+                **fac}
             # cfg2: ta01 N = 4096, masked-random
             e2 = JssVecEnv(4096, {"instance_path": "ta01"}, device=local_rank, auto_reset=True, seed=1)
             e2.reset()
@@ -434,6 +474,24 @@ def main():
                 "ta01 (15x15) N=4096, masked-random, one fused launch per step, obs/mask/reward/done written every step",
                 4096, ms, KC, b_alg(15, 15), peak, ln,
                 extra={"note": "5 MB per step: L2-resident and < 1 wave (4096 warps) -> launch/latency-bound by construction"})
+            # the same workload as a K-step fused device loop that RECORDS the trajectory: every transition's
+            # observation / mask / reward / done / action is kept in [K][N][...] buffers (jss_rollout_traj)
+            KR, reps = 256, 4
+            tr = e2.rollout_record("RANDOM", KR)
+            torch.cuda.synchronize()
+            l0 = e2.launch_count
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(reps):
+                tr = e2.rollout_record("RANDOM", KR, out=tr)
+            ev1.record()
+            torch.cuda.synchronize()
+            configs["cfg2_ta01_N4096_random_rollout_record"] = config_entry(
+                f"ta01 (15x15) N=4096, masked-random, {KR} transitions per launch in one fused device loop, EVERY transition's "
+                "obs/mask/reward/done/action recorded into [K][N][...] trajectory buffers",
+                4096, ev0.elapsed_time(ev1), KR * reps, b_alg(15, 15), peak, e2.launch_count - l0,
+                extra={"trajectory_bytes_per_env_step": 15 * 7 * 4 + int(e2._b.mask_stride) + 16 + 4})
+            del tr
             e2.close()
             del e2
             # cfg5: mixed ta01..ta80 N = 65536, on-device FIFO / MWR (+ masked-random for comparison)

@@ -66,6 +66,9 @@ extern "C" {
 /* jss_create flags */
 #define JSS_CREATE_AUTO_RESET 1u      /* step() on a done env resets it */
 #define JSS_CREATE_RECORD_SOLUTION 2u /* keep solution[N][Jmax][Mmax] start times (jss_env.py:163,454) */
+#define JSS_CREATE_HOST_MIRROR 4u     /* small batches (the single-env facade): action_mask, real_obs, the scalar records,
+                                         the x_* arrays and an action slot live in ONE pinned, device-mapped host block --
+                                         the kernels write results straight into host memory, no copies per transition */
 
 /* per-env flag bits (jss_buffers.flags_done >> 8) */
 #define JSS_FLAG_DONE 1u        /* _is_done() (jss_env.py:639-653) */
@@ -101,7 +104,7 @@ typedef struct jss_buffers {
     float *real_obs;        /* [N][J][7] fp32 (jss_env.py:102-111, 132)            */
     int32_t scalar_stride;  /* bytes between consecutive envs in the five per-env scalar arrays below
                                (they are fields of one 16-byte record per env, written with one store) */
-    int32_t reserved_;
+    int32_t host_mirror;    /* 1: the output pointers below are host-readable (JSS_CREATE_HOST_MIRROR) */
     float *reward;          /* [N] scaled reward (jss_env.py:483-493)              */
     int32_t *reward_raw;    /* [N] reward before scaling; -hole for ACTION_ADVANCE */
     uint8_t *done;          /* [N] 0/1 (low byte of flags_done)                    */
@@ -121,6 +124,7 @@ typedef struct jss_buffers {
     int32_t *x_tuam;        /* [N][M] time_until_available_machine        */
     uint8_t *x_legal;       /* [N][J] legal_actions[:-1]                  */
     uint8_t *x_blocked;     /* [N][J] action_illegal_no_op                */
+    int32_t *mirror_actions; /* [N] action slot inside the host block (JSS_CREATE_HOST_MIRROR), else NULL */
 } jss_buffers;
 
 /* number of int64 slots jss_stats() writes */
@@ -168,6 +172,10 @@ int jss_reset(jss_t *h, const uint8_t *env_mask_dev, void *stream);
  * actions_dev: device int32[N]. */
 int jss_step(jss_t *h, const int32_t *actions_dev, void *stream);
 
+/* jss_step() + jss_export_state() in ONE launch (generic kernel): the latency path of the single-env facade, which
+ * needs the decoded state after every transition to serve the reference's attribute surface. */
+int jss_step_export(jss_t *h, const int32_t *actions_dev, void *stream);
+
 /* Replaces DispatchingRule.__call__ (dispatching.py:92-408) / the masked-random
  * sampler (README.md:58-60).  Writes device int32[N] actions.  `step_index` is
  * the RNG counter (callers increment it per decision). */
@@ -190,6 +198,14 @@ int jss_step_sample(jss_t *h, const int32_t *actions_dev, int rule, int coin_mod
  * between steps; observations are written every step iff write_obs != 0. */
 int jss_rollout(jss_t *h, int rule, uint64_t seed, uint64_t step_index, int n_steps,
                 int write_obs, void *stream);
+
+/* jss_rollout() that also RECORDS the trajectory (what an on-policy collector wants from a rule / random policy):
+ * for k < n_steps and env e, slot k * N + e of the caller's device buffers receives the outputs of transition k --
+ * traj_obs [n_steps][N][J][7] fp32, traj_mask [n_steps][N][mask_stride] u8, traj_scalars [n_steps][N][4] int32
+ * (the 16-byte records), traj_actions [n_steps][N] int32 (the action taken; may be NULL).  The regular buffers hold
+ * the last transition afterwards, as after jss_rollout.  n_steps * N < 2^31. */
+int jss_rollout_traj(jss_t *h, int rule, uint64_t seed, uint64_t step_index, int n_steps, float *traj_obs,
+                     uint8_t *traj_mask, int32_t *traj_scalars, int32_t *traj_actions, void *stream);
 
 /* Host-buffer form of step(): copies actions H2D, steps, copies the results D2H with
  * contiguous DMA, synchronises.  Any output pointer may be NULL.  Host layouts equal the

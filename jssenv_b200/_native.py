@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libjss_b200.so")
 
 JSS_ABI_VERSION = 2
 ACTION_SKIP, ACTION_ADVANCE = -1, -2
-CREATE_AUTO_RESET, CREATE_RECORD_SOLUTION = 1, 2
+CREATE_AUTO_RESET, CREATE_RECORD_SOLUTION, CREATE_HOST_MIRROR = 1, 2, 4
 FLAG_DONE, FLAG_ERROR, FLAG_NOOP_LEGAL = 1, 2, 4
 COIN_DEVICE, COIN_NEVER = 0, 1
 WAIT_MASK, WAIT_OBS, WAIT_OBS_PREV = 1, 2, 3
@@ -28,19 +28,20 @@ EXPORTED_SYMBOLS = (
     "jss_get_buffers", "jss_instance_scalars", "jss_reset", "jss_step", "jss_policy", "jss_rollout",
     "jss_step_host", "jss_host_step_begin", "jss_host_wait", "jss_step_sample", "jss_stats", "jss_export_state", "jss_import_state", "jss_host_masked_random",
     "jss_launch_count", "jss_set_cr_due_date_factor", "jss_host_step_begin_packed", "jss_host_wire_stride",
-    "jss_host_expand_obs", "jss_host_configure", "jss_host_threads", "jss_host_set_simd",
+    "jss_host_expand_obs", "jss_host_configure", "jss_host_threads", "jss_host_set_simd", "jss_rollout_traj", "jss_step_export",
 )
 
 
 class JssBuffers(ctypes.Structure):
     _fields_ = [
         ("n_envs", c_int32), ("jobs_max", c_int32), ("machines_max", c_int32), ("mask_stride", c_int32),
-        ("action_mask", c_void_p), ("real_obs", c_void_p), ("scalar_stride", c_int32), ("reserved_", c_int32),
+        ("action_mask", c_void_p), ("real_obs", c_void_p), ("scalar_stride", c_int32), ("host_mirror", c_int32),
         ("reward", c_void_p), ("reward_raw", c_void_p),
         ("done", c_void_p), ("time", c_void_p), ("flags_done", c_void_p), ("solution", c_void_p),
         ("episode_count", c_void_p), ("last_makespan", c_void_p), ("last_return", c_void_p),
         ("x_todo", c_void_p), ("x_tufco", c_void_p), ("x_idle_last", c_void_p), ("x_total_idle", c_void_p),
         ("x_col4", c_void_p), ("x_tuam", c_void_p), ("x_legal", c_void_p), ("x_blocked", c_void_p),
+        ("mirror_actions", c_void_p),
     ]
 
 
@@ -76,6 +77,10 @@ def _declare(L):
     L.jss_host_expand_obs.restype = c_int
     L.jss_host_configure.argtypes = [c_int, c_int]
     L.jss_host_configure.restype = c_int
+    L.jss_rollout_traj.argtypes = [c_void_p, c_int, c_uint64, c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.jss_rollout_traj.restype = c_int
+    L.jss_step_export.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.jss_step_export.restype = c_int
     L.jss_host_set_simd.argtypes = [c_int]
     L.jss_host_set_simd.restype = c_int
     L.jss_host_threads.argtypes = []

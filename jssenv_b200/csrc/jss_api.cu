@@ -68,13 +68,16 @@ struct jss_handle {
 
     // device allocations
     std::vector<void *> allocs;
+    void *host_block = nullptr;                    // JSS_CREATE_HOST_MIRROR: pinned + mapped block behind the outputs
+    int32_t *mirror_actions = nullptr;
     JssInstDesc *d_inst = nullptr;
     uint16_t *d_ops = nullptr, *d_rem = nullptr;
+    uint8_t *d_pos = nullptr;
     int32_t *d_len = nullptr;
     unsigned long long *d_stats = nullptr;
 
     JssParams p{};
-    JssSmemLayout sl_norem{}, sl_rem{};
+    JssSmemLayout sl_env{}, sl_step{};               // shared-memory layouts of the generic / step kernels
     int class_tile_begin[3] = {0, 0, 0}, class_tile_end[3] = {0, 0, 0};  // KJ = 1, 2, 4
     int step_grid[16] = {0};                        // resident-CTA grids of the step kernel variants (filled lazily)
     bool use_pdl = true;
@@ -126,26 +129,17 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline int kj_of(int J) { return J <= 32 ? 1 : (J <= 64 ? 2 : 4); }
 inline int class_of(int kj) { return kj == 1 ? 0 : (kj == 2 ? 1 : 2); }
 
-size_t smem_bytes(const JssSmemLayout &sl) {
-    return sizeof(SmInst) + (size_t)sl.ops_elems * 2 + (size_t)sl.len_elems * 4 + (size_t)sl.rem_elems * 2 +
-           (size_t)JSS_WARPS_PER_CTA * sl.scratch_words * 4;
-}
+size_t smem_bytes(const JssSmemLayout &sl) { return (size_t)sl.off_warp0 + (size_t)JSS_WARPS_PER_CTA * sl.warp_stride; }
+
 void fill_uni(const JssInstDesc &d, SmInst &u) {
     u.J = d.J; u.M = d.M; u.max_time_op = d.max_time_op; u.max_time_jobs = d.max_time_jobs; u.sum_op = d.sum_op;
     u.f_mto = (float)d.max_time_op; u.f_mtj = (float)d.max_time_jobs; u.f_sop = (float)d.sum_op; u.f_M = (float)d.M;
     u.r_mto = d.r_mto; u.r_mtj = d.r_mtj; u.r_sop = d.r_sop; u.r_M = d.r_M;
     u.Jcap = round_up(d.J, 4); u.Mcap = round_up(d.M, 4); u.block_words = 5 * u.Jcap + u.Mcap + 12;
-}
-
-JssSmemLayout step_layout(jss_t *h, bool want_rem) {
-    JssSmemLayout sl = want_rem ? h->sl_rem : h->sl_norem;
-    sl.statein_words = h->p.block_words;
-    sl.off_len = (int32_t)sizeof(SmInst) + sl.ops_elems * 2;
-    sl.off_rem = sl.off_len + sl.len_elems * 4;
-    sl.off_warp0 = sl.off_rem + sl.rem_elems * 2;
-    sl.off_scratch = 16 + sl.statein_words * 4;
-    sl.warp_stride = sl.off_scratch + sl.scratch_words * 4 + sl.statein_words * 4;   // + state-out staging
-    return sl;
+    u.perm = d.perm;
+    u.y14[0] = u.y14[1] = u.f_mto; u.r14[0] = u.r14[1] = d.r_mto;
+    u.y23[0] = u.f_M; u.y23[1] = u.f_mtj; u.r23[0] = d.r_M; u.r23[1] = d.r_mtj;
+    u.y56[0] = u.y56[1] = u.f_sop; u.r56[0] = u.r56[1] = d.r_sop;
 }
 
 template <typename Kern>
@@ -169,8 +163,9 @@ int launch_step_uniform(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStre
     fill_uni(h->descs[h->p.uniform_inst], a.uni);
     a.tile_begin = 0;
     a.tile_end = (h->n_envs + JSS_WARPS_PER_CTA - 1) / JSS_WARPS_PER_CTA;
-    const JssSmemLayout sl = step_layout(h, want_rem);
-    const size_t smem = (size_t)sl.off_warp0 + (size_t)JSS_WARPS_PER_CTA * sl.warp_stride;
+    (void)want_rem;
+    const JssSmemLayout &sl = h->sl_step;
+    const size_t smem = smem_bytes(sl);
     auto kern = jss_step_kernel<KJ, SAMPLE>;
     const int slot = (KJ == 1 ? 0 : (KJ == 2 ? 1 : 2)) * 4 + SAMPLE + (want_rem ? 1 : 0);
     int rc = step_grid_for(h, kern, slot, smem);
@@ -187,8 +182,9 @@ int launch_step_uniform(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStre
 template <int SAMPLE>
 int launch_step_mixed(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStream_t st) {
     JssLaunch a = a_in;
-    const JssSmemLayout sl = step_layout(h, want_rem);
-    const size_t smem = (size_t)sl.off_warp0 + (size_t)JSS_WARPS_PER_CTA * sl.warp_stride;
+    (void)want_rem;
+    const JssSmemLayout &sl = h->sl_step;
+    const size_t smem = smem_bytes(sl);
     auto kern = jss_step_mixed_kernel<SAMPLE>;
     const int slot = 12 + SAMPLE + (want_rem ? 1 : 0);
     int rc = step_grid_for(h, kern, slot, smem);
@@ -250,8 +246,9 @@ int launch_class(jss_t *h, const JssLaunch &a, const JssSmemLayout &sl, cudaStre
 }
 
 int launch_all(jss_t *h, JssLaunch a, bool want_rem, cudaStream_t st) {
-    if (a.mode == JSS_MODE_STEP) return launch_step(h, a, st);   // one launch, whatever the mix of lane classes
-    const JssSmemLayout &sl = want_rem ? h->sl_rem : h->sl_norem;
+    if (a.mode == JSS_MODE_STEP && !a.export_after) return launch_step(h, a, st);   // one launch, whatever the mix of lane classes
+    (void)want_rem;
+    const JssSmemLayout &sl = h->sl_env;
     for (int c = 0; c < 3; c++) {
         a.tile_begin = h->class_tile_begin[c];
         a.tile_end = h->class_tile_end[c];
@@ -328,6 +325,7 @@ void jss_destroy(jss_t *h) {
         cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy);
     }
     for (void *ptr : h->allocs) cudaFree(ptr);
+    if (h->host_block) cudaFreeHost(h->host_block);
     delete h;
 }
 
@@ -339,6 +337,7 @@ int jss_load_instances(jss_t *h, int n_inst, const int32_t *jobs, const int32_t 
     if (n_inst >= (1 << 23)) return fail(h, JSS_ERR_UNSUPPORTED, "too many instances");
     JSS_CUDA(h, cudaSetDevice(h->device));
     std::vector<uint16_t> ops, rem;
+    std::vector<uint8_t> pos;
     std::vector<int32_t> len;
     h->insts.resize(n_inst);
     h->descs.resize(n_inst);
@@ -356,6 +355,9 @@ int jss_load_instances(jss_t *h, int n_inst, const int32_t *jobs, const int32_t 
         d.ops_off = (int32_t)ops.size();
         d.len_off = (int32_t)len.size();
         d.rem_off = (int32_t)rem.size();
+        d.pos_off = (int32_t)pos.size();
+        d.perm = 1;
+        pos.resize(pos.size() + round_up(J * M, 16), 0);
         ops.resize(ops.size() + round_up(J * M, 8), 0);
         len.resize(len.size() + round_up(J, 4), 0);
         rem.resize(rem.size() + round_up(J * (M + 1), 8), 0);
@@ -377,6 +379,14 @@ int jss_load_instances(jss_t *h, int n_inst, const int32_t *jobs, const int32_t 
             hi.len[j] = (int32_t)total;
             hi.sum_op += total;                                         // jss_env.py:88
             hi.max_time_jobs = std::max(hi.max_time_jobs, total);       // jss_env.py:89
+            {   // machine -> op index; a job that repeats / skips a machine makes the instance "general"
+                std::vector<int> seen((size_t)M, -1);
+                for (int i = 0; i < M; i++) {
+                    if (seen[mm[j * M + i]] >= 0) d.perm = 0;
+                    seen[mm[j * M + i]] = i;
+                }
+                for (int m = 0; m < M; m++) pos[d.pos_off + j * M + m] = (uint8_t)std::max(seen[m], 0);
+            }
             int64_t suffix = 0;
             rem[d.rem_off + j * (M + 1) + M] = 0;
             for (int i = M - 1; i >= 0; i--) {
@@ -399,6 +409,8 @@ int jss_load_instances(jss_t *h, int n_inst, const int32_t *jobs, const int32_t 
     if ((rc = dev_alloc(h, &h->d_ops, ops.size()))) return rc;
     if ((rc = dev_alloc(h, &h->d_len, len.size()))) return rc;
     if ((rc = dev_alloc(h, &h->d_rem, rem.size()))) return rc;
+    if ((rc = dev_alloc(h, &h->d_pos, pos.size()))) return rc;
+    JSS_CUDA(h, cudaMemcpy(h->d_pos, pos.data(), pos.size(), cudaMemcpyHostToDevice));
     JSS_CUDA(h, cudaMemcpy(h->d_inst, h->descs.data(), sizeof(JssInstDesc) * n_inst, cudaMemcpyHostToDevice));
     JSS_CUDA(h, cudaMemcpy(h->d_ops, ops.data(), ops.size() * 2, cudaMemcpyHostToDevice));
     JSS_CUDA(h, cudaMemcpy(h->d_len, len.data(), len.size() * 4, cudaMemcpyHostToDevice));
@@ -534,16 +546,24 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
         for (int e = 0; e < N; e++) uniform = uniform && env_to_inst[e] == env_to_inst[0];
         p.uniform_inst = uniform ? env_to_inst[0] : -1;   // then `order` is the identity (stable sort)
     }
-    p.inst = h->d_inst; p.ops_pool = h->d_ops; p.len_pool = h->d_len; p.rem_pool = h->d_rem;
+    p.inst = h->d_inst; p.ops_pool = h->d_ops; p.len_pool = h->d_len; p.rem_pool = h->d_rem; p.pos_pool = h->d_pos;
 
-    h->sl_norem.ops_elems = round_up(ops_max, 8);
-    h->sl_norem.len_elems = round_up(jmax, 4);
-    h->sl_norem.rem_elems = 0;
-    // observation staging (7 floats per job slot); env_check_no_op also keeps its 32-int per-warp
-    // machine-horizon table here, so never less than 32 words (tiny instances: 7 * Jcap < 32)
-    h->sl_norem.scratch_words = std::max(7 * p.Jcap, 32);
-    h->sl_rem = h->sl_norem;
-    h->sl_rem.rem_elems = round_up(rem_max, 8);
+    {   // shared-memory layouts: [SmInst][ops u16][len i32][rem u16][pos u8][per-warp regions], 16-byte aligned regions
+        JssSmemLayout sl{};
+        sl.off_len = (int32_t)sizeof(SmInst) + round_up(ops_max, 8) * 2;
+        sl.off_rem = sl.off_len + round_up(jmax, 4) * 4;
+        sl.off_pos = sl.off_rem + round_up(rem_max, 8) * 2;
+        sl.off_warp0 = sl.off_pos + round_up(ops_max, 16);
+        // observation staging (7 floats per job slot); env_check_no_op (general instances) also keeps its 32-int
+        // per-warp machine-horizon table here, so never less than 32 words (tiny instances: 7 * Jcap < 32)
+        sl.scratch_words = std::max(7 * p.Jcap, 32);
+        h->sl_env = sl;
+        h->sl_env.warp_stride = sl.scratch_words * 4;
+        h->sl_env.off_scratch = 0;
+        h->sl_step = sl;
+        h->sl_step.off_scratch = 16 + p.block_words * 4;                                   // [mbarrier][state-in]
+        h->sl_step.warp_stride = h->sl_step.off_scratch + sl.scratch_words * 4 + p.block_words * 4;   // [scratch][state-out]
+    }
 
     int rc;
     int32_t *d_order = nullptr;
@@ -568,9 +588,40 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
     p.hdr_off16 = d_hoff;
     const size_t NJ = (size_t)N * jmax, NM = (size_t)N * mmax;
     if ((rc = dev_alloc(h, &p.state, state_words))) return rc;
-    if ((rc = dev_alloc(h, &p.mask, (size_t)N * p.mask_stride))) return rc;
-    if ((rc = dev_alloc(h, &p.obs, NJ * 7))) return rc;
-    if ((rc = dev_alloc(h, &p.scalars, (size_t)N * 4))) return rc;
+    if (h->create_flags & JSS_CREATE_HOST_MIRROR) {
+        // every per-transition output in one pinned, device-mapped host block (unified addressing: the device
+        // pointer equals the host pointer); meant for small batches -- the kernels write over PCIe
+        size_t off = 0;
+        auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+        const size_t o_mask = take(N * (size_t)p.mask_stride), o_obs = take(NJ * 7 * 4), o_sc = take((size_t)N * 16);
+        const size_t o_i[5] = {take(NJ * 4), take(NJ * 4), take(NJ * 4), take(NJ * 4), take(NJ * 4)};
+        const size_t o_tuam = take(NM * 4), o_legal = take(NJ), o_blocked = take(NJ), o_act = take((size_t)N * 4);
+        JSS_CUDA(h, cudaHostAlloc(&h->host_block, off, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(h->host_block, 0, off);
+        void *dev = nullptr;
+        JSS_CUDA(h, cudaHostGetDevicePointer(&dev, h->host_block, 0));
+        if (dev != h->host_block) return fail(h, JSS_ERR_CUDA, "host mirror needs unified addressing");
+        char *b = static_cast<char *>(h->host_block);
+        p.mask = reinterpret_cast<uint8_t *>(b + o_mask); p.obs = reinterpret_cast<float *>(b + o_obs);
+        p.scalars = reinterpret_cast<int32_t *>(b + o_sc);
+        p.x_todo = reinterpret_cast<int32_t *>(b + o_i[0]); p.x_tufco = reinterpret_cast<int32_t *>(b + o_i[1]);
+        p.x_idle_last = reinterpret_cast<int32_t *>(b + o_i[2]); p.x_total_idle = reinterpret_cast<int32_t *>(b + o_i[3]);
+        p.x_col4 = reinterpret_cast<int32_t *>(b + o_i[4]); p.x_tuam = reinterpret_cast<int32_t *>(b + o_tuam);
+        p.x_legal = reinterpret_cast<uint8_t *>(b + o_legal); p.x_blocked = reinterpret_cast<uint8_t *>(b + o_blocked);
+        h->mirror_actions = reinterpret_cast<int32_t *>(b + o_act);
+    } else {
+        if ((rc = dev_alloc(h, &p.mask, (size_t)N * p.mask_stride))) return rc;
+        if ((rc = dev_alloc(h, &p.obs, NJ * 7))) return rc;
+        if ((rc = dev_alloc(h, &p.scalars, (size_t)N * 4))) return rc;
+        if ((rc = dev_alloc(h, &p.x_todo, NJ))) return rc;
+        if ((rc = dev_alloc(h, &p.x_tufco, NJ))) return rc;
+        if ((rc = dev_alloc(h, &p.x_idle_last, NJ))) return rc;
+        if ((rc = dev_alloc(h, &p.x_total_idle, NJ))) return rc;
+        if ((rc = dev_alloc(h, &p.x_col4, NJ))) return rc;
+        if ((rc = dev_alloc(h, &p.x_tuam, NM))) return rc;
+        if ((rc = dev_alloc(h, &p.x_legal, NJ))) return rc;
+        if ((rc = dev_alloc(h, &p.x_blocked, NJ))) return rc;
+    }
     if (h->create_flags & JSS_CREATE_RECORD_SOLUTION) {
         if ((rc = dev_alloc(h, &p.solution, NJ * mmax, false))) return rc;
         JSS_CUDA(h, cudaMemset(p.solution, 0xff, NJ * mmax * 4));  // -1
@@ -581,14 +632,6 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
     if ((rc = dev_alloc(h, &p.last_makespan, (size_t)N))) return rc;
     if ((rc = dev_alloc(h, &p.last_return, (size_t)N))) return rc;
     if ((rc = dev_alloc(h, &p.acc, (size_t)N * 4))) return rc;
-    if ((rc = dev_alloc(h, &p.x_todo, NJ))) return rc;
-    if ((rc = dev_alloc(h, &p.x_tufco, NJ))) return rc;
-    if ((rc = dev_alloc(h, &p.x_idle_last, NJ))) return rc;
-    if ((rc = dev_alloc(h, &p.x_total_idle, NJ))) return rc;
-    if ((rc = dev_alloc(h, &p.x_col4, NJ))) return rc;
-    if ((rc = dev_alloc(h, &p.x_tuam, NM))) return rc;
-    if ((rc = dev_alloc(h, &p.x_legal, NJ))) return rc;
-    if ((rc = dev_alloc(h, &p.x_blocked, NJ))) return rc;
     if ((rc = dev_alloc(h, &h->d_stats, (size_t)JSS_STATS_LEN))) return rc;
     if ((rc = dev_alloc(h, &h->dev_actions, (size_t)N))) return rc;
     h->assigned = true;
@@ -604,6 +647,8 @@ int jss_get_buffers(jss_t *h, jss_buffers *out) {
     out->n_envs = p.n_envs; out->jobs_max = p.jobs_max; out->machines_max = p.machines_max;
     out->mask_stride = p.mask_stride;
     out->action_mask = p.mask; out->real_obs = p.obs; out->solution = p.solution;
+    out->host_mirror = h->host_block ? 1 : 0;
+    out->mirror_actions = h->mirror_actions;
     out->scalar_stride = 16;   // reward / reward_raw / time / flags_done are fields of one 16-byte record per env
     out->reward = reinterpret_cast<float *>(p.scalars); out->reward_raw = p.scalars + 1;
     out->time = p.scalars + 2; out->flags_done = reinterpret_cast<uint32_t *>(p.scalars + 3);
@@ -631,6 +676,17 @@ int jss_step(jss_t *h, const int32_t *actions_dev, void *stream) {
     JssLaunch a{};
     a.mode = JSS_MODE_STEP;
     a.actions = actions_dev;
+    return launch_all(h, a, false, (cudaStream_t)stream);
+}
+
+int jss_step_export(jss_t *h, const int32_t *actions_dev, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!actions_dev) return fail(h, JSS_ERR_INVALID, "jss_step_export: actions_dev is NULL");
+    JssLaunch a{};
+    a.mode = JSS_MODE_STEP;
+    a.actions = actions_dev;
+    a.export_after = 1;
     return launch_all(h, a, false, (cudaStream_t)stream);
 }
 
@@ -671,6 +727,22 @@ int jss_rollout(jss_t *h, int rule, uint64_t seed, uint64_t step_index, int n_st
     a.mode = JSS_MODE_ROLLOUT;
     a.rule = rule; a.coin_mode = JSS_COIN_DEVICE; a.seed = seed; a.step_index = step_index; a.cr_factor = h->cr_factor;
     a.n_steps = n_steps; a.write_obs = write_obs;
+    return launch_all(h, a, rule_wants_rem(rule), (cudaStream_t)stream);
+}
+
+int jss_rollout_traj(jss_t *h, int rule, uint64_t seed, uint64_t step_index, int n_steps, float *traj_obs,
+                     uint8_t *traj_mask, int32_t *traj_scalars, int32_t *traj_actions, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (rule < 0 || rule >= JSS_NUM_RULES || n_steps < 0 || !traj_obs || !traj_mask || !traj_scalars)
+        return fail(h, JSS_ERR_INVALID, "jss_rollout_traj: bad arguments (rule %d, n_steps %d)", rule, n_steps);
+    if ((int64_t)n_steps * h->n_envs >= INT32_MAX)
+        return fail(h, JSS_ERR_UNSUPPORTED, "jss_rollout_traj: n_steps * n_envs must stay below 2^31");
+    JssLaunch a{};
+    a.mode = JSS_MODE_ROLLOUT;
+    a.rule = rule; a.coin_mode = JSS_COIN_DEVICE; a.seed = seed; a.step_index = step_index; a.cr_factor = h->cr_factor;
+    a.n_steps = n_steps; a.write_obs = 1;
+    a.traj_obs = traj_obs; a.traj_mask = traj_mask; a.traj_scalars = traj_scalars; a.traj_actions = traj_actions;
     return launch_all(h, a, rule_wants_rem(rule), (cudaStream_t)stream);
 }
 

@@ -41,6 +41,7 @@ struct InstView {  // instance tables staged in shared memory
     const uint16_t *ops;
     const int32_t *len;
     const uint16_t *rem;
+    const uint8_t *pos;
     const SmInst *si;
 };
 
@@ -86,6 +87,27 @@ JSS_DEV float jss_div(float x, float y, float ry) {
     const float r = __fmaf_rn(-q, y, x);
     return __fmaf_rn(r, ry, q);
 }
+
+// two quotients at once on the packed-fp32 pipe (sm_100 FMUL2 / FFMA2): the same three roundings per element
+// as jss_div, so the results are identical
+#ifndef JSS_EMU
+JSS_DEV float2 jss_div2(float2 x, const float (&y)[2], const float (&ry)[2]) {
+    unsigned long long xx, yy, rr, q, e, o;
+    xx = *reinterpret_cast<unsigned long long *>(&x);
+    const float2 yv = make_float2(y[0], y[1]), rv = make_float2(ry[0], ry[1]);
+    yy = *reinterpret_cast<const unsigned long long *>(&yv);
+    rr = *reinterpret_cast<const unsigned long long *>(&rv);
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q) : "l"(xx), "l"(rr));
+    asm("{\n .reg .b64 nq;\n .reg .b32 lo, hi;\n mov.b64 {lo, hi}, %1;\n xor.b32 lo, lo, 0x80000000;\n xor.b32 hi, hi, 0x80000000;\n"
+        " mov.b64 nq, {lo, hi};\n fma.rn.f32x2 %0, nq, %2, %3;\n}" : "=l"(e) : "l"(q), "l"(yy), "l"(xx));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(o) : "l"(e), "l"(rr), "l"(q));
+    return *reinterpret_cast<float2 *>(&o);
+}
+#else
+JSS_DEV float2 jss_div2(float2 x, const float (&y)[2], const float (&ry)[2]) {
+    return make_float2(jss_div(x.x, y[0], ry[0]), jss_div(x.y, y[1], ry[1]));
+}
+#endif
 
 // ---- TMA (cp.async.bulk) + mbarrier helpers -----------------------------------------------
 // The state block of the NEXT env of a warp is prefetched into the warp's shared-memory
@@ -403,6 +425,44 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
             maxh = max(maxh, cur);                      // :321
         }
     }
+    const int last = iv.si->M - 1;
+    if (iv.si->perm) {
+        // Permutation instance (every job visits every machine exactly once): the walk of pass 2 (:324-401) can be
+        // answered per legal machine in closed form.  A job that starts walking at op ts0 and time tm0 reaches its
+        // op on machine m -- op index k = pos[j][m] -- at  tm0 + sum(dur[ts0 .. k-1]) = tm0 + rem[ts0] - rem[k]  (suffix
+        // sums), provided ts0 <= k < M-1; the walk's stop test `max_horizon > time` cannot fire before that because
+        // max_horizon >= the horizon of every legal machine (it is the running maximum of their prefix minima) and
+        // times only grow along the walk.  So machine m joins machine_next (:351 / :391) iff its horizon lies beyond
+        // that arrival time: branch-free, at most 3 legal machines, no divergent per-lane loops.
+        uint32_t want = 0u;
+#pragma unroll
+        for (int i = 0; i < KJ; i++) {
+            const int tq = __shfl_sync(JSS_FULL, s.tuam, (int)(jss_op_m(s.op[i]) & 31u));   // countdown of the job's machine
+            const bool running = s.tufco[i] > 0;
+            // walkers: jobs that are not legal and either running (case 1, :327-337) or idle and not blocked by a
+            // no-op (case 2, :366-377); finished / padding slots (todo == M) never walk
+            const bool walker = !(s.lb & (1u << i)) && s.todo[i] < iv.si->M && (running || !(s.lb & (16u << i)));
+            const int ts0 = s.todo[i] + (running ? 1 : 0);
+            const int tm0 = s.t + (running ? s.tufco[i] : tq);
+            const int j = min(KJ * lane + i, iv.si->J - 1);
+            const uint16_t *rem_j = iv.rem + j * (iv.si->M + 1);
+            const uint8_t *pos_j = iv.pos + j * iv.si->M;
+            const int base = tm0 + (int)rem_j[min(ts0, iv.si->M)];
+#define JSS_NOOP_PROBE(LM, H)                                                                           \
+            if (LM >= 0) {                               /* warp-uniform */                             \
+                const int k = (int)pos_j[LM];                                                           \
+                const int arrive = base - (int)rem_j[k];                                                \
+                want |= (uint32_t)(walker && k >= ts0 && k < last && H > arrive) << LM;                 \
+            }
+            JSS_NOOP_PROBE(lm0, h0)
+            JSS_NOOP_PROBE(lm1, h1)
+            JSS_NOOP_PROBE(lm2, h2)
+#undef JSS_NOOP_PROBE
+        }
+        want = __reduce_or_sync(JSS_FULL, want);
+        return ML != 0u && want == ML;                  // len(machine_next) == nb_machine_legal
+    }
+    // general instance (a job may visit a machine twice / never): literal walks.
     // per-machine horizon table: finite only for machines that have a legal job, so the
     // walk's test `max_horizon_machine[m] > time and machine_legal[m]` is one compare
     hz[lane] = (lane == lm0) ? h0 : (lane == lm1) ? h1 : (lane == lm2) ? h2 : (int)0x80000000;
@@ -410,7 +470,6 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
     // pass 2 (:324-401): jobs that are not legal now but may need a legal machine soon
     uint32_t want = 0u;
     const int row = KJ * lane * iv.si->M;
-    const int last = iv.si->M - 1;
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
         // countdown of the job's current machine (case 2, :374-377)
@@ -455,12 +514,13 @@ JSS_DEV void env_emit_obs(const JssParams &p, const InstView &iv, const EnvRegs<
             const int len = iv.len[KJ * lane + i];        // unconditional (in-bounds) load + select
             const int perf = (s.todo[i] < iv.si->M) ? s.t - s.total_idle[i] : len;
             v[7 * i + 0] = (s.lb & (1u << i)) ? 1.0f : 0.0f;
-            v[7 * i + 1] = jss_div((float)s.tufco[i], iv.si->f_mto, iv.si->r_mto);
-            v[7 * i + 2] = jss_div((float)s.todo[i], iv.si->f_M, iv.si->r_M);
-            v[7 * i + 3] = jss_div((float)perf, iv.si->f_mtj, iv.si->r_mtj);
-            v[7 * i + 4] = jss_div((float)s.col4[i], iv.si->f_mto, iv.si->r_mto);
-            v[7 * i + 5] = jss_div((float)s.idle_last[i], iv.si->f_sop, iv.si->r_sop);
-            v[7 * i + 6] = jss_div((float)s.total_idle[i], iv.si->f_sop, iv.si->r_sop);
+            // columns that share a divisor (or sit next to each other) go through the packed-fp32 pipe in pairs
+            const float2 q14 = jss_div2(make_float2((float)s.tufco[i], (float)s.col4[i]), iv.si->y14, iv.si->r14);
+            const float2 q23 = jss_div2(make_float2((float)s.todo[i], (float)perf), iv.si->y23, iv.si->r23);
+            const float2 q56 = jss_div2(make_float2((float)s.idle_last[i], (float)s.total_idle[i]), iv.si->y56, iv.si->r56);
+            v[7 * i + 1] = q14.x; v[7 * i + 4] = q14.y;
+            v[7 * i + 2] = q23.x; v[7 * i + 3] = q23.y;
+            v[7 * i + 5] = q56.x; v[7 * i + 6] = q56.y;
         }
         // stage the lane's 7*KJ floats (one contiguous, bank-conflict-free run per lane) ...
         float *mine = scratch + 7 * KJ * lane;
@@ -778,42 +838,78 @@ JSS_DEV void env_pack(const JssLaunch &a, const InstView &iv, const EnvRegs<KJ> 
 }
 
 // ---- CTA-level driver -----------------------------------------------------------------------
-struct JssSmemLayout {      // element counts; every region starts 16-byte aligned
-    int32_t ops_elems, len_elems, rem_elems, scratch_words;
-    int32_t statein_words;  // step kernel only: per-warp state-block prefetch buffer
-    // byte offsets from the start of dynamic shared memory, precomputed on the host so the
-    // kernel derives every pointer with one add: [SmInst][ops][len][rem][per-warp regions]
-    int32_t off_len, off_rem, off_warp0, warp_stride, off_scratch;   // off_scratch: inside a warp region
+struct JssSmemLayout {
+    // byte offsets from the start of dynamic shared memory, precomputed on the host so the kernels derive every
+    // pointer with one add (each region 16-byte aligned): [SmInst][ops u16][len i32][rem u16][pos u8][per-warp regions]
+    int32_t off_len, off_rem, off_pos, off_warp0;
+    int32_t warp_stride;    // bytes per warp region
+    int32_t scratch_words;  // observation staging (7 floats per job slot), >= 32 words
+    int32_t off_scratch;    // step kernels: [mbarrier 16 B][state-in block][scratch][state-out block]; else 0
+    int32_t pad_;
 };
 
-JSS_DEV void jss_stage_instance(const JssParams &p, const JssInstDesc &d, SmInst *si, uint16_t *sm_ops,
-                                int32_t *sm_len, uint16_t *sm_rem, bool want_rem, bool want_tables = true) {
+struct JssCtaSmem {         // the CTA-shared part
+    SmInst *si;
+    uint16_t *ops;
+    int32_t *len;
+    uint16_t *rem;
+    uint8_t *pos;
+};
+JSS_DEV void jss_cta_carve(const JssSmemLayout &sl, char *sm, JssCtaSmem &c, InstView &iv) {
+    c.si = reinterpret_cast<SmInst *>(sm);
+    c.ops = reinterpret_cast<uint16_t *>(sm + sizeof(SmInst));
+    c.len = reinterpret_cast<int32_t *>(sm + sl.off_len);
+    c.rem = reinterpret_cast<uint16_t *>(sm + sl.off_rem);
+    c.pos = reinterpret_cast<uint8_t *>(sm + sl.off_pos);
+    iv.ops = c.ops; iv.len = c.len; iv.rem = c.rem; iv.pos = c.pos; iv.si = c.si;
+}
+
+#define JSS_STAGE_OPS 1     // ops + jobs_length
+#define JSS_STAGE_REM 2     // suffix sums (rules MWR / LWR / CR, _check_no_op on permutation instances)
+#define JSS_STAGE_POS 4     // machine -> op index (_check_no_op on permutation instances)
+#define JSS_STAGE_ALL 7
+
+JSS_DEV void jss_fill_sminst(const JssInstDesc &d, SmInst *si) {
+    si->J = d.J; si->M = d.M; si->max_time_op = d.max_time_op; si->max_time_jobs = d.max_time_jobs;
+    si->sum_op = d.sum_op;
+    si->f_mto = (float)d.max_time_op; si->f_mtj = (float)d.max_time_jobs; si->f_sop = (float)d.sum_op;
+    si->f_M = (float)d.M;
+    si->r_mto = d.r_mto; si->r_mtj = d.r_mtj; si->r_sop = d.r_sop; si->r_M = d.r_M;
+    si->Jcap = (d.J + 3) & ~3; si->Mcap = (d.M + 3) & ~3; si->block_words = 5 * si->Jcap + si->Mcap + 12;
+    si->perm = d.perm;
+    si->y14[0] = si->y14[1] = si->f_mto; si->r14[0] = si->r14[1] = d.r_mto;
+    si->y23[0] = si->f_M; si->y23[1] = si->f_mtj; si->r23[0] = d.r_M; si->r23[1] = d.r_mtj;
+    si->y56[0] = si->y56[1] = si->f_sop; si->r56[0] = si->r56[1] = d.r_sop;
+}
+
+JSS_DEV void jss_stage_instance(const JssParams &p, const JssInstDesc &d, const JssCtaSmem &c, int what) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    if (tid == 0) {
-        si->J = d.J; si->M = d.M; si->max_time_op = d.max_time_op; si->max_time_jobs = d.max_time_jobs;
-        si->sum_op = d.sum_op;
-        si->f_mto = (float)d.max_time_op; si->f_mtj = (float)d.max_time_jobs; si->f_sop = (float)d.sum_op;
-        si->f_M = (float)d.M;
-        si->r_mto = d.r_mto; si->r_mtj = d.r_mtj; si->r_sop = d.r_sop; si->r_M = d.r_M;
-        si->Jcap = (d.J + 3) & ~3; si->Mcap = (d.M + 3) & ~3; si->block_words = 5 * si->Jcap + si->Mcap + 12;
+    if (tid == 0) jss_fill_sminst(d, c.si);
+    // pools are padded so whole uint4 copies stay in-bounds
+    if (what & JSS_STAGE_OPS) {
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.ops_pool + d.ops_off);
+            uint4 *dst = reinterpret_cast<uint4 *>(c.ops);
+            const int n = (d.J * d.M + 7) >> 3;
+            for (int k = tid; k < n; k += nt) dst[k] = src[k];
+        }
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.len_pool + d.len_off);
+            uint4 *dst = reinterpret_cast<uint4 *>(c.len);
+            const int n = (d.J + 3) >> 2;
+            for (int k = tid; k < n; k += nt) dst[k] = src[k];
+        }
     }
-    if (!want_tables) return;
-    {   // pools are padded so whole uint4 copies stay in-bounds
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.ops_pool + d.ops_off);
-        uint4 *dst = reinterpret_cast<uint4 *>(sm_ops);
-        const int n = (d.J * d.M + 7) >> 3;
-        for (int k = tid; k < n; k += nt) dst[k] = src[k];
-    }
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.len_pool + d.len_off);
-        uint4 *dst = reinterpret_cast<uint4 *>(sm_len);
-        const int n = (d.J + 3) >> 2;
-        for (int k = tid; k < n; k += nt) dst[k] = src[k];
-    }
-    if (want_rem) {
+    if (what & JSS_STAGE_REM) {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.rem_pool + d.rem_off);
-        uint4 *dst = reinterpret_cast<uint4 *>(sm_rem);
+        uint4 *dst = reinterpret_cast<uint4 *>(c.rem);
         const int n = (d.J * (d.M + 1) + 7) >> 3;
+        for (int k = tid; k < n; k += nt) dst[k] = src[k];
+    }
+    if ((what & JSS_STAGE_POS) && d.perm) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.pos_pool + d.pos_off);
+        uint4 *dst = reinterpret_cast<uint4 *>(c.pos);
+        const int n = (d.J * d.M + 15) >> 4;
         for (int k = tid; k < n; k += nt) dst[k] = src[k];
     }
 }
@@ -882,24 +978,43 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
                     make_int4(0, 0, s.t, (int)((s.flags << 8) | (s.flags & JSS_FLAG_DONE)));
             }
         }
+        if (a.export_after) env_export<KJ>(p, iv, s, env, lane);   // single-env facade: one launch per transition
         return;
     }
     // JSS_MODE_ROLLOUT: n_steps x (policy -> step) with the state held in registers
     bool dirty = false;
     int raw = 0;
-    for (int k = 0; k < a.n_steps; k++) {
-        const uint32_t h = jss_hash3(a.seed, genv, a.step_index + (uint64_t)k);
-        const int act = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
-        int r = 0;
-        const bool changed = env_step<KJ>(p, iv, s, env, lane, act, r, hz);
-        if (changed) {
-            raw = r; dirty = true;
-            if (a.write_obs) env_emit_all<KJ>(p, iv, s, env, lane, scratch, r);
+    if (a.traj_obs) {
+        // trajectory recording: step k of this env writes its observation / mask / scalar record (and the action that
+        // led to it) into slot k * n_envs + env of the caller's [n_steps][N][...] buffers -- the emit helpers index
+        // their outputs by env only, so a shifted index is all it takes
+        JssParams pt = p;
+        pt.obs = a.traj_obs; pt.mask = a.traj_mask; pt.scalars = a.traj_scalars;
+        for (int k = 0; k < a.n_steps; k++) {
+            const uint32_t h = jss_hash3(a.seed, genv, a.step_index + (uint64_t)k);
+            const int act = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
+            int r = 0;
+            const bool changed = env_step<KJ>(p, iv, s, env, lane, act, r, hz);
+            if (changed) { raw = r; dirty = true; }
+            const int slot = k * p.n_envs + env;
+            if (a.traj_actions && lane == 0) a.traj_actions[slot] = act;
+            env_emit_all<KJ>(pt, iv, s, slot, lane, scratch, changed ? r : 0);
+        }
+    } else {
+        for (int k = 0; k < a.n_steps; k++) {
+            const uint32_t h = jss_hash3(a.seed, genv, a.step_index + (uint64_t)k);
+            const int act = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
+            int r = 0;
+            const bool changed = env_step<KJ>(p, iv, s, env, lane, act, r, hz);
+            if (changed) {
+                raw = r; dirty = true;
+                if (a.write_obs) env_emit_all<KJ>(p, iv, s, env, lane, scratch, r);
+            }
         }
     }
     if (dirty) {
         env_store<KJ>(p, iv, env, lane, s);
-        if (!a.write_obs) env_emit_all<KJ>(p, iv, s, env, lane, scratch, raw);
+        if (!a.write_obs || a.traj_obs) env_emit_all<KJ>(p, iv, s, env, lane, scratch, raw);
     }
 }
 
@@ -919,28 +1034,30 @@ JSS_DEV void jss_tile_desc(const JssParams &p, int tile, int &first, int &inst, 
 #endif
 
 template <int KJ, int MODE>
-__global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, (MODE == JSS_MODE_STEP) ? JSS_MIN_CTAS : 1)
+__global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, 1)
 jss_env_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JSS_SMEM_DECL(jss_smem);
-    SmInst *si = reinterpret_cast<SmInst *>(jss_smem);
-    uint16_t *sm_ops = reinterpret_cast<uint16_t *>(si + 1);
-    int32_t *sm_len = reinterpret_cast<int32_t *>(sm_ops + sl.ops_elems);
-    uint16_t *sm_rem = reinterpret_cast<uint16_t *>(sm_len + sl.len_elems);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *scratch = reinterpret_cast<float *>(sm_rem + sl.rem_elems) + (size_t)warp * sl.scratch_words;
-    const bool want_rem = (MODE == JSS_MODE_POLICY || MODE == JSS_MODE_ROLLOUT) &&
-                          (a.rule == JSS_RULE_MWR || a.rule == JSS_RULE_LWR || a.rule == JSS_RULE_CR);
-    int staged = -1;
+    char *sm = reinterpret_cast<char *>(jss_smem);
+    JssCtaSmem c;
     InstView iv;
-    iv.ops = sm_ops; iv.len = sm_len; iv.rem = sm_rem; iv.si = si;
-    // the masked-uniform sampler looks at no instance table at all (only J)
-    const bool want_tables = !(MODE == JSS_MODE_POLICY && a.rule == JSS_RULE_RANDOM);
+    jss_cta_carve(sl, sm, c, iv);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *scratch = reinterpret_cast<float *>(sm + sl.off_warp0 + warp * sl.warp_stride);
+    // what the mode reads: the masked-uniform sampler looks at no instance table at all (only J); the other policies
+    // at ops / len (+ suffix sums for MWR / LWR / CR); everything that steps needs all tables
+    int what = JSS_STAGE_OPS;
+    if (MODE == JSS_MODE_ROLLOUT || a.mode == JSS_MODE_STEP) what = JSS_STAGE_ALL;
+    if (MODE == JSS_MODE_POLICY)
+        what = a.rule == JSS_RULE_RANDOM ? 0
+             : (a.rule == JSS_RULE_MWR || a.rule == JSS_RULE_LWR || a.rule == JSS_RULE_CR) ? (JSS_STAGE_OPS | JSS_STAGE_REM)
+             : JSS_STAGE_OPS;
+    int staged = -1;
     for (int tile = a.tile_begin + (int)blockIdx.x; tile < a.tile_end; tile += (int)gridDim.x) {
         int first, inst, count;
         jss_tile_desc(p, tile, first, inst, count);
         if (inst != staged) {                            // CTA-uniform
             __syncthreads();
-            jss_stage_instance(p, p.inst[inst], si, sm_ops, sm_len, sm_rem, want_rem, want_tables);
+            jss_stage_instance(p, p.inst[inst], c, what);
             staged = inst;
             __syncthreads();
         }
@@ -1010,9 +1127,9 @@ JSS_DEV void jss_tile_state(const JssParams &p, const SmInst *uni, int tile, int
 
 // tiles tile, tile + tile_step, ... < tile_end of ONE lane class through the prefetch pipeline
 template <int KJ, int SAMPLE, bool UNI>
-JSS_DEV void jss_step_tiles(const JssParams &p, const JssLaunch &a, const JssSmemLayout &sl, InstView &iv, SmInst *si,
-                            uint16_t *sm_ops, int32_t *sm_len, uint16_t *sm_rem, const JssWarpSmem &w, int warp,
-                            int lane, int tile, int tile_end, int tile_step, int &staged, uint32_t &phase) {
+JSS_DEV void jss_step_tiles(const JssParams &p, const JssLaunch &a, const JssSmemLayout &sl, InstView &iv,
+                            const JssCtaSmem &c, const JssWarpSmem &w, int warp, int lane, int tile, int tile_end,
+                            int tile_step, int &staged, uint32_t &phase) {
     int env_next, act_next = 0;
     {
         uint32_t off16, blk16;
@@ -1027,7 +1144,7 @@ JSS_DEV void jss_step_tiles(const JssParams &p, const JssLaunch &a, const JssSme
             const int inst = p.tiles[tile].inst_count >> 8;
             if (inst != staged) {                        // CTA-uniform
                 __syncthreads();
-                jss_stage_instance(p, p.inst[inst], si, sm_ops, sm_len, sm_rem, SAMPLE == 2 && sl.rem_elems > 0);
+                jss_stage_instance(p, p.inst[inst], c, JSS_STAGE_ALL);
                 staged = inst;
                 __syncthreads();
             }
@@ -1096,27 +1213,25 @@ __global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, JSS_MIN_CTAS)
 jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JSS_SMEM_DECL(jss_smem);
     char *sm = reinterpret_cast<char *>(jss_smem);
-    SmInst *si = reinterpret_cast<SmInst *>(sm);
-    uint16_t *sm_ops = reinterpret_cast<uint16_t *>(sm + sizeof(SmInst));
-    int32_t *sm_len = reinterpret_cast<int32_t *>(sm + sl.off_len);
-    uint16_t *sm_rem = reinterpret_cast<uint16_t *>(sm + sl.off_rem);
+    JssCtaSmem c;
+    InstView iv;
+    jss_cta_carve(sl, sm, c, iv);
+    iv.si = &a.uni;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     JssWarpSmem w;
     jss_step_carve(sl, sm, warp, w);
     if (lane == 0) jss_mbar_init(w.mbar);
-    InstView iv;
-    iv.ops = sm_ops; iv.len = sm_len; iv.rem = sm_rem; iv.si = &a.uni;
     jss_pdl_launch_dependents();
     // prologue on read-only data (overlaps the tail of the previous launch under PDL)
-    jss_stage_instance(p, p.inst[p.uniform_inst], si, sm_ops, sm_len, sm_rem, SAMPLE == 2 && sl.rem_elems > 0);
+    jss_stage_instance(p, p.inst[p.uniform_inst], c, JSS_STAGE_ALL);
     __syncthreads();
     jss_pdl_wait();
     int staged = p.uniform_inst;
     uint32_t phase = 0;
     // Static strided tiles; the env after the current one is known one iteration ahead, which is what
     // the TMA prefetch needs.
-    jss_step_tiles<KJ, SAMPLE, true>(p, a, sl, iv, si, sm_ops, sm_len, sm_rem, w, warp, lane,
-                                     a.tile_begin + (int)blockIdx.x, a.tile_end, (int)gridDim.x, staged, phase);
+    jss_step_tiles<KJ, SAMPLE, true>(p, a, sl, iv, c, w, warp, lane, a.tile_begin + (int)blockIdx.x, a.tile_end,
+                                     (int)gridDim.x, staged, phase);
     if (lane == 0) jss_bulk_store_wait_all();            // shared memory must outlive the bulk reads
 }
 
@@ -1131,24 +1246,21 @@ __global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, JSS_MIN_CTAS)
 jss_step_mixed_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JSS_SMEM_DECL(jss_smem);
     char *sm = reinterpret_cast<char *>(jss_smem);
-    SmInst *si = reinterpret_cast<SmInst *>(sm);
-    uint16_t *sm_ops = reinterpret_cast<uint16_t *>(sm + sizeof(SmInst));
-    int32_t *sm_len = reinterpret_cast<int32_t *>(sm + sl.off_len);
-    uint16_t *sm_rem = reinterpret_cast<uint16_t *>(sm + sl.off_rem);
+    JssCtaSmem c;
+    InstView iv;
+    jss_cta_carve(sl, sm, c, iv);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     JssWarpSmem w;
     jss_step_carve(sl, sm, warp, w);
     if (lane == 0) jss_mbar_init(w.mbar);
-    InstView iv;
-    iv.ops = sm_ops; iv.len = sm_len; iv.rem = sm_rem; iv.si = si;
     jss_pdl_launch_dependents();
     const int4 r = *reinterpret_cast<const int4 *>(p.cta_ranges + blockIdx.x);   // tile cuts: [x,y) KJ=4, [y,z) KJ=2, [z,w) KJ=1
     jss_pdl_wait();
     int staged = -1;
     uint32_t phase = 0;
-    jss_step_tiles<4, SAMPLE, false>(p, a, sl, iv, si, sm_ops, sm_len, sm_rem, w, warp, lane, r.x, r.y, 1, staged, phase);
-    jss_step_tiles<2, SAMPLE, false>(p, a, sl, iv, si, sm_ops, sm_len, sm_rem, w, warp, lane, r.y, r.z, 1, staged, phase);
-    jss_step_tiles<1, SAMPLE, false>(p, a, sl, iv, si, sm_ops, sm_len, sm_rem, w, warp, lane, r.z, r.w, 1, staged, phase);
+    jss_step_tiles<4, SAMPLE, false>(p, a, sl, iv, c, w, warp, lane, r.x, r.y, 1, staged, phase);
+    jss_step_tiles<2, SAMPLE, false>(p, a, sl, iv, c, w, warp, lane, r.y, r.z, 1, staged, phase);
+    jss_step_tiles<1, SAMPLE, false>(p, a, sl, iv, c, w, warp, lane, r.z, r.w, 1, staged, phase);
     if (lane == 0) jss_bulk_store_wait_all();            // shared memory must outlive the bulk reads
 }
 

@@ -39,11 +39,13 @@ class JssEnv(_gym.Env if _gym is not None else object):
     def __init__(self, env_config: Optional[Dict[str, Any]] = None, device: int = 0):
         if env_config is None:
             env_config = {"instance_path": DEFAULT_INSTANCE}   # jss_env.py:35-38
-        self._vec = JssVecEnv(1, {"instance_path": env_config["instance_path"]}, device=device,
-                              record_solution=True)
+        # a batch of ONE env whose outputs live in a pinned, device-mapped host block (JSS_CREATE_HOST_MIRROR): a
+        # transition is one kernel launch + one stream sync, and the attributes below are numpy reads of that block
+        self._vec = JssVecEnv(1, {"instance_path": env_config["instance_path"]}, device=device, host_mirror=True)
         machine, duration = self._vec.instances[0]
         self.jobs, self.machines = int(machine.shape[0]), int(machine.shape[1])
         self.instance_matrix = np.stack([machine, duration], axis=-1).astype(np.int64)   # (J, M, 2), jss_env.py:78
+        self._machine_of = machine.astype(np.int64)
         self.jobs_length = duration.sum(axis=1).astype(np.int64)
         self.max_time_op, self.max_time_jobs, self.sum_op = (int(v) for v in self._vec.instance_scalars[0])
         self.last_solution = None
@@ -59,55 +61,77 @@ class JssEnv(_gym.Env if _gym is not None else object):
             self.observation_space = _Space("Dict", spaces={
                 "action_mask": _Space("Box", low=0, high=1, shape=(J + 1,)),
                 "real_obs": _Space("Box", low=0.0, high=1.0, shape=(J, 7), dtype=float)})
-        self._fresh = False
+        self.solution = np.full((self.jobs, self.machines), -1, dtype=np.int64)       # jss_env.py:163
+        self._arange = np.arange(J)
+        self._vec._L.jss_export_state(self._vec._h, self._vec._stream())
         self._pull()
 
     # ------------------------------------------------------------------ state mirror
     def _pull(self):
-        """Copy the env's device state to the host and rebuild the reference's attributes."""
+        """Read the env's decoded state from the host mirror (written by the device kernels) and rebuild the reference's
+        primary attributes; the redundant ones are derived lazily, see __getattr__."""
         v = self._vec
-        x = v.export_state()
         v.synchronize()
-        J, M = self.jobs, self.machines
-        g = lambda t: t[0].cpu().numpy()                      # noqa: E731
-        todo = g(x["todo"]).astype(np.int64)
-        tufco = g(x["tufco"]).astype(np.int64)
-        tuam = g(x["tuam"]).astype(np.int64)
-        self.todo_time_step_job = todo
-        self.time_until_finish_current_op_jobs = tufco
-        self.time_until_available_machine = tuam
-        self.idle_time_jobs_last_op = g(x["idle_last"]).astype(np.int64)
-        self.total_idle_time_jobs = g(x["total_idle"]).astype(np.int64)
-        self.action_illegal_no_op = g(x["blocked"]).astype(bool)
-        self.current_time_step = int(v.current_time_step[0])
-        flags = int(v.flags[0])
-        self._flags = flags
-        legal = np.zeros(J + 1, dtype=bool)
-        legal[:J] = g(x["legal"]).astype(bool)
-        legal[J] = bool(flags & N.FLAG_NOOP_LEGAL)
+        h = v.host
+        self.todo_time_step_job = h["todo"][0].astype(np.int64)
+        self.time_until_finish_current_op_jobs = h["tufco"][0].astype(np.int64)
+        self.time_until_available_machine = h["tuam"][0].astype(np.int64)
+        self.idle_time_jobs_last_op = h["idle_last"][0].astype(np.int64)
+        self.total_idle_time_jobs = h["total_idle"][0].astype(np.int64)
+        self.action_illegal_no_op = h["blocked"][0].astype(bool)
+        sc = h["scalars"][0]
+        self.current_time_step = int(sc[2])
+        self._flags = int(sc[3]) >> 8
+        self._reward_raw = int(sc[1])
+        legal = np.empty(self.jobs + 1, dtype=bool)
+        legal[: self.jobs] = h["legal"][0]
+        legal[self.jobs] = bool(self._flags & N.FLAG_NOOP_LEGAL)
         self.legal_actions = legal
-        unfinished = todo < M
-        safe = np.minimum(todo, M - 1)
-        ar = np.arange(J)
-        self.needed_machine_jobs = np.where(unfinished, self.instance_matrix[ar, safe, 0], -1).astype(np.int64)
-        # total_perform = t - total_idle until the job completes (then jobs_length)
-        self.total_perform_op_time_jobs = np.where(
-            unfinished, self.current_time_step - self.total_idle_time_jobs, self.jobs_length).astype(np.int64)
-        ml = np.zeros(M, dtype=bool)
-        ml[self.needed_machine_jobs[legal[:J]]] = True         # machine_legal == "some legal job needs it"
-        self.machine_legal = ml
-        self.nb_machine_legal = int(ml.sum())
-        self.nb_legal_actions = int(legal[:J].sum())
-        ia = np.zeros((M, J), dtype=bool)                      # illegal_actions[m][j] == blocked[j] & needed[j]==m
-        bj = np.flatnonzero(self.action_illegal_no_op)
-        ia[self.needed_machine_jobs[bj], bj] = True
-        self.illegal_actions = ia
-        # event queue == sorted set {t + tuam[m] : tuam[m] > 0} (appendix A.1)
-        self.next_time_step = sorted({int(self.current_time_step + d) for d in tuam if d > 0})
-        self.next_jobs = [int(np.flatnonzero((tufco > 0) & (self.current_time_step + tufco == e))[0])
-                          for e in self.next_time_step]
-        self.solution = v.solution[0].cpu().numpy().astype(np.int64)
-        self.state = v.real_obs[0].cpu().numpy().astype(np.float64)
+        self.state = h["real_obs"][0].astype(np.float64)
+        self._derived = {}
+
+    # redundant reference state, re-derived on first access after a transition
+    def _derive(self, name):
+        J, M = self.jobs, self.machines
+        if name == "needed_machine_jobs":
+            todo = self.todo_time_step_job
+            val = np.where(todo < M, self._machine_of[self._arange, np.minimum(todo, M - 1)], -1).astype(np.int64)
+        elif name == "total_perform_op_time_jobs":
+            # total_perform = t - total_idle until the job completes (then jobs_length)
+            val = np.where(self.todo_time_step_job < M, self.current_time_step - self.total_idle_time_jobs,
+                           self.jobs_length).astype(np.int64)
+        elif name == "machine_legal":
+            val = np.zeros(M, dtype=bool)
+            val[self.needed_machine_jobs[self.legal_actions[:J]]] = True    # machine_legal == "some legal job needs it"
+        elif name == "nb_machine_legal":
+            val = int(self.machine_legal.sum())
+        elif name == "nb_legal_actions":
+            val = int(self.legal_actions[:J].sum())
+        elif name == "illegal_actions":
+            val = np.zeros((M, J), dtype=bool)                               # illegal_actions[m][j] == blocked[j] & needed[j]==m
+            bj = np.flatnonzero(self.action_illegal_no_op)
+            val[self.needed_machine_jobs[bj], bj] = True
+        elif name == "next_time_step":
+            # event queue == sorted set {t + tuam[m] : tuam[m] > 0} (appendix A.1)
+            val = sorted({int(self.current_time_step + d) for d in self.time_until_available_machine if d > 0})
+        elif name == "next_jobs":
+            tufco = self.time_until_finish_current_op_jobs
+            val = [int(np.flatnonzero((tufco > 0) & (self.current_time_step + tufco == e))[0]) for e in self.next_time_step]
+        else:
+            raise AttributeError(name)
+        self._derived[name] = val
+        return val
+
+    _DERIVED = ("needed_machine_jobs", "total_perform_op_time_jobs", "machine_legal", "nb_machine_legal",
+                "nb_legal_actions", "illegal_actions", "next_time_step", "next_jobs")
+
+    def __getattr__(self, name):
+        if name in JssEnv._DERIVED:
+            d = self.__dict__.get("_derived")
+            if d is None:
+                raise AttributeError(name)
+            return d[name] if name in d else self._derive(name)
+        raise AttributeError(name)
 
     def _raise_for_error(self, message):
         """The device error bit is sticky; the facade turns it into the reference's IndexError once and
@@ -115,11 +139,17 @@ class JssEnv(_gym.Env if _gym is not None else object):
         snap = self._vec.export_state()
         snap["flags"].bitwise_and_(~((N.FLAG_ERROR) << 8))
         self._vec.import_state(snap)
+        self._vec._L.jss_export_state(self._vec._h, self._vec._stream())
         self._pull()
         raise IndexError(message)
 
     def _get_current_state_representation(self):
         return {"real_obs": self.state, "action_mask": self.legal_actions}
+
+    def _transition(self, action: int):
+        self._vec.host["actions"][0] = action
+        self._vec.step_export_host()          # one launch (step + decode) and one sync
+        self._pull()
 
     # ------------------------------------------------------------------ reference API
     def get_legal_actions(self):
@@ -128,6 +158,8 @@ class JssEnv(_gym.Env if _gym is not None else object):
     def reset(self, *, seed=None, options=None):
         """Returns the observation only, like the reference (jss_env.py:145-181)."""
         self._vec.reset()
+        self._vec._L.jss_export_state(self._vec._h, self._vec._stream())
+        self.solution = np.full((self.jobs, self.machines), -1, dtype=np.int64)
         self._pull()
         return self._get_current_state_representation()
 
@@ -135,16 +167,19 @@ class JssEnv(_gym.Env if _gym is not None else object):
         a = int(action)
         if not (0 <= a <= self.jobs):
             raise IndexError(f"action {a} out of range")
-        self._vec.step(np.array([a], dtype=np.int32))
-        self._pull()
+        t_before = self.current_time_step
+        op_before = int(self.todo_time_step_job[a]) if a < self.jobs else -1
+        self._transition(a)
         if self._flags & N.FLAG_ERROR:
             # the reference raises IndexError here (jss_env.py:444 / :517) or silently corrupts
             # its counters (illegal job action); the device env sets the sticky error bit
             self._raise_for_error(f"illegal action {a} for the current state")
+        if a < self.jobs:
+            self.solution[a][op_before] = t_before             # jss_env.py:454
         # float64 quotient like the reference's _reward_scaler (jss_env.py:483-493); the device record holds the
         # exact integer numerator next to its fp32 quotient
-        reward = float(int(self._vec.reward_raw[0])) / float(self.max_time_op)
-        done = bool(self._vec.done[0])
+        reward = float(self._reward_raw) / float(self.max_time_op)
+        done = bool(self._flags & N.FLAG_DONE)
         if done:                                               # jss_env.py:649-652
             self.last_time_step = self.current_time_step
             self.last_solution = self.solution
@@ -152,19 +187,19 @@ class JssEnv(_gym.Env if _gym is not None else object):
 
     def increase_time_step(self) -> int:
         """Raw time advance without the legal-action heuristics (jss_env.py:495-637)."""
-        self._vec.step(np.array([N.ACTION_ADVANCE], dtype=np.int32))
-        self._pull()
+        self._transition(N.ACTION_ADVANCE)
         if self._flags & N.FLAG_ERROR:
             self._raise_for_error("pop from empty list")      # what the reference raises (jss_env.py:517)
-        return -int(self._vec.reward_raw[0])
+        return -self._reward_raw
 
     def set_cr_due_date_factor(self, factor: float):
         self._vec.set_cr_due_date_factor(factor)
 
     def rule_action(self, rule: str):
         """(action, noop_legal) chosen on device by a dispatching rule, without the 10 % coin."""
-        a = self._vec.policy(rule, coin="never")
-        return int(a[0]), bool(self._flags & N.FLAG_NOOP_LEGAL)
+        self._vec.policy(rule, coin="never", out=self._vec._mirror_actions)   # lands in the host-mapped action slot
+        self._vec.synchronize()
+        return int(self._vec.host["actions"][0]), bool(self._flags & N.FLAG_NOOP_LEGAL)
 
     def render(self, mode: str = "human"):
         """Gantt rows of the current solution (jss_env.py:655-693 builds a plotly figure from the

@@ -31,7 +31,8 @@ def _instance_list(env_config: Optional[Dict[str, Any]]):
 
 class JssVecEnv:
     def __init__(self, num_envs: int, env_config: Optional[Dict[str, Any]] = None, device: int = 0,
-                 auto_reset: bool = False, record_solution: bool = False, env_id_base: int = 0, seed: int = 0):
+                 auto_reset: bool = False, record_solution: bool = False, env_id_base: int = 0, seed: int = 0,
+                 host_mirror: bool = False):
         self._h = ctypes.c_void_p()
         self._L = N.backend.library()
         self.num_envs = int(num_envs)
@@ -42,7 +43,8 @@ class JssVecEnv:
         self._step_index = 0
         insts, env_to_inst = _instance_list(env_config)
         self.instances = insts
-        flags = (N.CREATE_AUTO_RESET if auto_reset else 0) | (N.CREATE_RECORD_SOLUTION if record_solution else 0)
+        flags = ((N.CREATE_AUTO_RESET if auto_reset else 0) | (N.CREATE_RECORD_SOLUTION if record_solution else 0) |
+                 (N.CREATE_HOST_MIRROR if host_mirror else 0))
         rc = self._L.jss_create(ctypes.byref(self._h), self.device_index, self.num_envs, flags, self.env_id_base)
         N.check(None, rc, "jss_create")
         # instance tables (jss_env.py:72-95)
@@ -96,6 +98,29 @@ class JssVecEnv:
             "col4": w(b.x_col4, (n, J), np.int32, d), "tuam": w(b.x_tuam, (n, M), np.int32, d),
             "legal": w(b.x_legal, (n, J), np.uint8, d), "blocked": w(b.x_blocked, (n, J), np.uint8, d),
         }
+        self.host = None
+        if b.host_mirror:
+            # JSS_CREATE_HOST_MIRROR: the same memory seen from the host (pinned, device-mapped): numpy views, no copies
+            def hv(ptr, shape, dt, strides=None):
+                dt = np.dtype(dt)
+                nbytes = (int(np.prod(shape)) * dt.itemsize if strides is None
+                          else sum((sh - 1) * st for sh, st in zip(shape, strides)) + dt.itemsize)
+                raw = np.frombuffer((ctypes.c_char * nbytes).from_address(int(ptr)), dtype=np.uint8)
+                if strides is None:
+                    return raw.view(dt).reshape(shape)
+                return np.lib.stride_tricks.as_strided(raw[: nbytes // dt.itemsize * dt.itemsize].view(dt) if dt.itemsize > 1 else raw,
+                                                       shape=shape, strides=strides)
+            sc = hv(b.reward, (n, 4), np.int32)
+            self.host = {
+                "action_mask": hv(b.action_mask, (n, J + 1), np.uint8, strides=(int(b.mask_stride), 1)),
+                "real_obs": hv(b.real_obs, (n, J, 7), np.float32), "scalars": sc,
+                "todo": hv(b.x_todo, (n, J), np.int32), "tufco": hv(b.x_tufco, (n, J), np.int32),
+                "idle_last": hv(b.x_idle_last, (n, J), np.int32), "total_idle": hv(b.x_total_idle, (n, J), np.int32),
+                "col4": hv(b.x_col4, (n, J), np.int32), "tuam": hv(b.x_tuam, (n, M), np.int32),
+                "legal": hv(b.x_legal, (n, J), np.uint8), "blocked": hv(b.x_blocked, (n, J), np.uint8),
+                "actions": hv(b.mirror_actions, (n,), np.int32),
+            }
+            self._mirror_actions = w(b.mirror_actions, (n,), np.int32, d)
         self._truncated = torch.zeros(n, dtype=torch.bool, device=self.device)
         self._actions = torch.zeros(n, dtype=torch.int32, device=self.device)
 
@@ -142,6 +167,14 @@ class JssVecEnv:
         N.check(self._h, self._L.jss_step(self._h, ctypes.c_void_p(a.data_ptr()), self._stream()), "jss_step")
         return self._obs(), self.reward, self.done, self._truncated, {}
 
+    def step_export_host(self):
+        """Host-mirror batches (the single-env facade): apply the actions written to ``self.host["actions"]`` and decode
+        the new state into the x_* arrays in ONE launch (jss_step_export), then wait; afterwards every array of
+        ``self.host`` is current.  No per-transition copies: the kernels write straight into the pinned block."""
+        rc = self._L.jss_step_export(self._h, ctypes.c_void_p(self._mirror_actions.data_ptr()), self._stream())
+        N.check(self._h, rc, "jss_step_export")
+        N.backend.synchronize(self.device_index)
+
     def step_sample(self, actions, rule: Union[str, int] = "RANDOM", coin: str = "device", out=None):
         """step(actions) fused with policy(rule) for the next decision (one launch): returns the usual
         step tuple plus the int32[N] tensor of next actions (`out`, default: in place of `actions`)."""
@@ -186,6 +219,35 @@ class JssVecEnv:
         N.check(self._h, rc, "jss_rollout")
         self._step_index += int(n_steps)
         return self._obs(), self.reward, self.done, self._truncated, {}
+
+    def rollout_record(self, rule: Union[str, int], n_steps: int, out: Optional[Dict[str, Any]] = None):
+        """n_steps x (policy -> step) fused on device WITH the trajectory recorded (jss_rollout_traj): returns
+        {"real_obs": (K, N, J, 7) f32, "action_mask": (K, N, J+1) bool, "reward": (K, N) f32, "done": (K, N) bool,
+        "actions": (K, N) i32, ...} as device tensors; pass the dict back as `out` to reuse the buffers."""
+        import torch
+        r = N.RULES[rule.upper()] if isinstance(rule, str) else int(rule)
+        K, n, J, ms = int(n_steps), self.num_envs, self.jobs, int(self._b.mask_stride)
+        if out is None or out["_obs"].shape[0] != K:
+            dev = self.device
+            # zero-filled once: rows of envs with fewer jobs than the batch maximum are only written up to J_i
+            out = {"_obs": torch.zeros((K, n, J, 7), dtype=torch.float32, device=dev),
+                   "_mask": torch.zeros((K, n, ms), dtype=torch.uint8, device=dev),
+                   "_scalars": torch.zeros((K, n, 4), dtype=torch.int32, device=dev),
+                   "actions": torch.zeros((K, n), dtype=torch.int32, device=dev)}
+            out["real_obs"] = out["_obs"]
+            out["action_mask"] = out["_mask"][:, :, : J + 1].view(torch.bool)
+            out["reward"] = out["_scalars"][:, :, 0].view(torch.float32)
+            out["reward_raw"] = out["_scalars"][:, :, 1]
+            out["time"] = out["_scalars"][:, :, 2]
+            out["done"] = (out["_scalars"][:, :, 3] & 1).bool() if N.backend.name != "cuda" else None
+        rc = self._L.jss_rollout_traj(self._h, r, self.seed, self._step_index, K,
+                                      ctypes.c_void_p(out["_obs"].data_ptr()), ctypes.c_void_p(out["_mask"].data_ptr()),
+                                      ctypes.c_void_p(out["_scalars"].data_ptr()), ctypes.c_void_p(out["actions"].data_ptr()),
+                                      self._stream())
+        N.check(self._h, rc, "jss_rollout_traj")
+        self._step_index += K
+        out["done"] = (out["_scalars"][:, :, 3] & 1).bool()       # lazily evaluated view of the done bit
+        return out
 
     # ---------------------------------------------------------------- host-buffer form
     def step_host(self, actions: np.ndarray, want_obs: bool = True):

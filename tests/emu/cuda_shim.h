@@ -119,6 +119,8 @@ static inline cudaError_t cudaSetDevice(int) { return 0; }
 static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? 0 : 2; }
 static inline cudaError_t cudaFree(void *p) { free(p); return 0; }
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
+enum { cudaHostAllocMapped = 2, cudaHostAllocPortable = 1 };
+static inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { *p = aligned_alloc(256, (n + 255) / 256 * 256); return *p ? 0 : 2; }
 static inline cudaError_t cudaMemset(void *p, int v, size_t n) { memset(p, v, n); return 0; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return 0; }

@@ -677,3 +677,24 @@ def check_shard_invariance(make_env, n_total=24, n_steps=350, seed=77):
             for s in shards:
                 s.close()
             whole.close()
+
+
+def check_rollout_record(make_env, names, rule, n_steps, seed):
+    """jss_rollout_traj: slot k of the recorded trajectory == the outputs after transition k of policy + step."""
+    uniq = sorted(set(names))
+    cfg = {"instance_paths": uniq, "env_to_instance": [uniq.index(n) for n in names]}
+    a_env = make_env(len(names), cfg, seed=seed, auto_reset=True)
+    b_env = make_env(len(names), cfg, seed=seed, auto_reset=True)
+    a_env.reset(); b_env.reset()
+    tr = a_env.rollout_record(rule, n_steps)
+    for k in range(n_steps):
+        acts = b_env.policy(rule)
+        assert np.array_equal(_np(tr["actions"][k]), _np(acts)), k
+        b_env.step(acts)
+        assert np.array_equal(_np(tr["action_mask"][k]), _np(b_env.action_mask)), k
+        assert np.array_equal(_np(tr["real_obs"][k]), _np(b_env.real_obs)), k
+        assert np.array_equal(_np(tr["reward"][k]), _np(b_env.reward)) and np.array_equal(_np(tr["done"][k]), _np(b_env.done)), k
+        assert np.array_equal(_np(tr["time"][k]), _np(b_env.current_time_step)), k
+    for name in ("action_mask", "real_obs", "reward", "done", "current_time_step", "episode_count", "last_makespan"):
+        assert np.array_equal(_np(getattr(a_env, name)), _np(getattr(b_env, name))), name
+    assert a_env.stats() == b_env.stats()

@@ -149,3 +149,8 @@ def test_emu_shard_invariance():
 def test_emu_host_pipeline_packed():
     pc.check_host_pipeline_packed(make_env, ["ta01", "ta31", "ta51", "ta80", "dmu16"], seed=5)
     pc.check_host_pipeline_packed(make_env, ["ta80"] * 3, seed=6)
+
+
+@pytest.mark.parametrize("rule", ["RANDOM", "FIFO"])
+def test_emu_rollout_record(rule):
+    pc.check_rollout_record(make_env, ["ta01", "ta01", "ta51", "ta80"], rule, n_steps=300, seed=3)

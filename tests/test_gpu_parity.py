@@ -281,3 +281,8 @@ def test_gpu_shard_invariance():
 def test_gpu_host_pipeline_packed():
     pc.check_host_pipeline_packed(make_env, ["ta01", "ta11", "ta31", "ta51", "ta62", "ta80", "dmu16"] * 9, seed=5, n_steps=600)
     pc.check_host_pipeline_packed(make_env, ["ta80"] * 3, seed=6)
+
+
+@pytest.mark.parametrize("rule", ["RANDOM", "FIFO"])
+def test_gpu_rollout_record(rule):
+    pc.check_rollout_record(make_env, ["ta01"] * 5 + ["ta31", "ta51", "ta80", "ta80"], rule, n_steps=2500, seed=3)
