@@ -407,15 +407,27 @@ def main():
         bound = JssVecEnv.host_configure(0, local_rank)   # pool = usable CPUs / local ranks, on the GPU's NUMA node
         threads = int(env._L.jss_host_threads())
 
+        phase = {}
+
         def run_e2e(packed, steps):
             mask = np.ascontiguousarray(env.action_mask.cpu().numpy())
             env.host_step_begin(env.host_masked_random(mask, 0), packed=packed)
             checksum = 0.0
+            ph = [0.0, 0.0, 0.0, 0.0]
+            clock = time.perf_counter
 
             def e2e_step(k):
+                t0 = clock()
                 m, rew, dn = env.host_wait_mask()
-                env.host_step_begin(env.host_masked_random(m, k), packed=packed)
-                return env.host_wait_obs(previous=True)      # the step's observation, fp32 on the host
+                t1 = clock()
+                a_next = env.host_masked_random(m, k)
+                t2 = clock()
+                env.host_step_begin(a_next, packed=packed)
+                t3 = clock()
+                o = env.host_wait_obs(previous=True)         # the step's observation, fp32 on the host
+                t4 = clock()
+                ph[0] += t1 - t0; ph[1] += t2 - t1; ph[2] += t3 - t2; ph[3] += t4 - t3
+                return o
 
             for k in range(1, 4):
                 e2e_step(k)
@@ -431,6 +443,10 @@ def main():
             dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            n_calls = steps + 3
+            phase["packed" if packed else "fp32_dma"] = {
+                "wait_mask_ms": ph[0] / n_calls * 1e3, "host_policy_ms": ph[1] / n_calls * 1e3,
+                "begin_ms": ph[2] / n_calls * 1e3, "wait_obs_and_expand_ms": ph[3] / n_calls * 1e3}
             return world * N * steps / float(dt.item())
 
         ms_b, ws_b = int(env._b.mask_stride), int(env._L.jss_host_wire_stride(env._h))
@@ -441,6 +457,7 @@ def main():
                "d2h_bytes_per_step": N * ms_b + N * ws_b + 16 * N,
                "steps": args.e2e_steps, "host_threads": threads, "numa_bound_cpus": bound,
                "fp32_dma_variant": {"value": v_plain, "d2h_bytes_per_step": N * ms_b + N * J * 7 * 4 + 16 * N},
+               "host_ms_per_step": phase,
                "note": "jss_host_step_begin_packed / jss_host_wait / jss_host_expand_obs (pinned host buffers): H2D actions, step "
                        "kernel, D2H mask + scalar records + packed integer observation rows (10 B per job) every step, expansion "
                        "to the exact fp32 (N, J, 7) observation by the host pool and the host masked-random policy inside the "

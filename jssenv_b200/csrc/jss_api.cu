@@ -190,6 +190,11 @@ int launch_step_mixed(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStream
     int rc = step_grid_for(h, kern, slot, smem);
     if (rc) return rc;
     const int grid = h->p.n_cta_ranges;                   // one static equal-cost range per CTA (all resident: SMs x 3)
+    {
+        static const bool sm_major = !(getenv("JSS_MIXED_MAP") && getenv("JSS_MIXED_MAP")[0] == '0');
+        const int per_sm = grid / h->sm_count;
+        if (sm_major && per_sm >= 1 && per_sm * h->sm_count == grid) { a.range_sms = h->sm_count; a.range_per_sm = per_sm; }
+    }
     if (h->use_pdl) JSS_CUDA(h, JSS_LAUNCH_PDL(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl));
     else JSS_LAUNCH(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl);
     JSS_CUDA(h, cudaGetLastError());

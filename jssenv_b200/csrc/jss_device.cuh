@@ -1032,6 +1032,9 @@ JSS_DEV void jss_tile_desc(const JssParams &p, int tile, int &first, int &inst, 
 #ifndef JSS_MIN_CTAS
 #define JSS_MIN_CTAS 3   // 78 registers, no spills -> 3 CTAs = 24 warps per SM (sweeps in profiles/)
 #endif
+#ifndef JSS_MIN_CTAS_SMALL
+#define JSS_MIN_CTAS_SMALL JSS_MIN_CTAS   // uniform batches with <= 64 jobs (KJ = 1, 2): latency-bound, may want more warps
+#endif
 
 template <int KJ, int MODE>
 __global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, 1)
@@ -1209,7 +1212,7 @@ JSS_DEV void jss_step_carve(const JssSmemLayout &sl, char *sm, int warp, JssWarp
 // Uniform batch (every env runs the same instance): static strided tiles, the per-instance scalars are
 // read from the kernel parameters (constant-bank operands), no CTA barrier after the first staging.
 template <int KJ, int SAMPLE>
-__global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, JSS_MIN_CTAS)
+__global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, KJ == 4 ? JSS_MIN_CTAS : JSS_MIN_CTAS_SMALL)
 jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JSS_SMEM_DECL(jss_smem);
     char *sm = reinterpret_cast<char *>(jss_smem);
@@ -1254,7 +1257,13 @@ jss_step_mixed_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout 
     jss_step_carve(sl, sm, warp, w);
     if (lane == 0) jss_mbar_init(w.mbar);
     jss_pdl_launch_dependents();
-    const int4 r = *reinterpret_cast<const int4 *>(p.cta_ranges + blockIdx.x);   // tile cuts: [x,y) KJ=4, [y,z) KJ=2, [z,w) KJ=1
+    // Which range?  Ranges are consecutive in (class, instance) order, and CTAs b, b + #SMs, b + 2 #SMs normally share
+    // an SM (the block scheduler deals the resident grid out round-robin): giving them CONSECUTIVE ranges makes the
+    // CTAs of one SM run the same lane class, i.e. one 40-60 KB loop body per SM instead of all three (130 KB) fighting
+    // over the instruction cache.  Correctness does not depend on the placement -- it is a fixed permutation.
+    int ridx = (int)blockIdx.x;
+    if (a.range_sms > 0) ridx = ((int)blockIdx.x % a.range_sms) * a.range_per_sm + (int)blockIdx.x / a.range_sms;
+    const int4 r = *reinterpret_cast<const int4 *>(p.cta_ranges + ridx);   // tile cuts: [x,y) KJ=4, [y,z) KJ=2, [z,w) KJ=1
     jss_pdl_wait();
     int staged = -1;
     uint32_t phase = 0;

@@ -298,23 +298,62 @@ void jss_host_parallel_for(int64_t n, int64_t grain, void (*fn)(int64_t, int64_t
     Pool::get().parallel_for(n, grain, [&](int64_t b, int64_t e) { fn(b, e, ctx); });
 }
 
+#ifdef JSS_HAVE_AVX2_TARGET
+// one mask row: count the set bytes and return the index of the r-th one, 32 bytes at a time (the row may be read up
+// to the next multiple of 32 past `width` only if that stays inside the row stride)
+__attribute__((target("avx2,bmi2,popcnt"))) int pick_row_avx2(const uint8_t *row, int width, uint32_t h) {
+    uint32_t bits[8];                                     // width <= 129 -> at most 5 words of 32 mask bytes
+    const int nw = (width + 31) >> 5;
+    const __m256i zero = _mm256_setzero_si256();
+    int cnt = 0;
+    for (int w = 0; w < nw; w++) {
+        const int left = width - 32 * w;
+        __m256i v;
+        if (left >= 32) v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(row + 32 * w));
+        else {
+            alignas(32) uint8_t tmp[32] = {0};
+            memcpy(tmp, row + 32 * w, (size_t)left);
+            v = _mm256_load_si256(reinterpret_cast<const __m256i *>(tmp));
+        }
+        bits[w] = ~(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, zero));
+        cnt += __builtin_popcount(bits[w]);
+    }
+    if (cnt == 0) return -1;
+    uint32_t r = jss_pick(h, (uint32_t)cnt);
+    for (int w = 0; w < nw; w++) {
+        const uint32_t c = (uint32_t)__builtin_popcount(bits[w]);
+        if (r < c) return 32 * w + (int)__builtin_ctz(_pdep_u32(1u << r, bits[w]));
+        r -= c;
+    }
+    return -1;
+}
+bool have_bmi2() { static const bool v = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2"); return v; }
+#endif
+
 void jss_host_masked_random_impl(const uint8_t *mask_host, int n, int width, int64_t row_stride, uint64_t seed,
                                  uint64_t env_id_base, uint64_t step_index, int32_t *actions_host) {
     auto work = [&](int64_t lo, int64_t hi) {
         for (int64_t e = lo; e < hi; e++) {
             const uint8_t *row = mask_host + (size_t)e * (size_t)row_stride;
+            const uint32_t hsh = jss_hash3(seed, env_id_base + (uint64_t)e, step_index);
+#ifdef JSS_HAVE_AVX2_TARGET
+            if (width <= 256 && have_bmi2() && g_simd_cap.load(std::memory_order_relaxed) >= 1) {
+                actions_host[e] = pick_row_avx2(row, width, hsh);
+                continue;
+            }
+#endif
             int cnt = 0;
             for (int i = 0; i < width; i++) cnt += row[i] != 0;
             int act = -1;   // JSS_ACTION_SKIP
             if (cnt > 0) {
-                uint32_t r = jss_pick(jss_hash3(seed, env_id_base + (uint64_t)e, step_index), (uint32_t)cnt);
+                uint32_t r = jss_pick(hsh, (uint32_t)cnt);
                 for (int i = 0; i < width; i++)
                     if (row[i]) { if (r == 0) { act = i; break; } r--; }
             }
             actions_host[e] = act;
         }
     };
-    if ((int64_t)n * width < (1 << 18)) { work(0, n); return; }
+    if ((int64_t)n * width < (1 << 16)) { work(0, n); return; }
     Pool::get().parallel_for(n, 1024, work);
 }
 

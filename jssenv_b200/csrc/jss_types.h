@@ -103,6 +103,7 @@ struct JssLaunch {           // per-launch arguments
     int32_t tile_begin, tile_end;
     int32_t mode;            // JSS_MODE_*
     int32_t rule, coin_mode, n_steps, write_obs;
+    int32_t range_sms, range_per_sm;   // mixed step kernel: CTA -> range permutation (0: identity)
     int32_t export_after;    // step through the generic kernel: also decode the new state into the x_* arrays (facade)
     uint64_t seed, step_index;
     double cr_factor;        // CriticalRatio due_date_factor (dispatching.py:337-349); reference default 1.5
