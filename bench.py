@@ -409,9 +409,9 @@ def main():
 
         phase = {}
 
-        def run_e2e(packed, steps):
+        def run_e2e(packed, steps, dma_fraction=0.0):
             mask = np.ascontiguousarray(env.action_mask.cpu().numpy())
-            env.host_step_begin(env.host_masked_random(mask, 0), packed=packed)
+            env.host_step_begin(env.host_masked_random(mask, 0), packed=packed, dma_fraction=dma_fraction)
             checksum = 0.0
             ph = [0.0, 0.0, 0.0, 0.0]
             clock = time.perf_counter
@@ -422,7 +422,7 @@ def main():
                 t1 = clock()
                 a_next = env.host_masked_random(m, k)
                 t2 = clock()
-                env.host_step_begin(a_next, packed=packed)
+                env.host_step_begin(a_next, packed=packed, dma_fraction=dma_fraction)
                 t3 = clock()
                 o = env.host_wait_obs(previous=True)         # the step's observation, fp32 on the host
                 t4 = clock()
@@ -444,24 +444,38 @@ def main():
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             n_calls = steps + 3
-            phase["packed" if packed else "fp32_dma"] = {
+            phase[("hybrid %.2f" % dma_fraction if dma_fraction > 0 else "packed") if packed else "fp32_dma"] = {
                 "wait_mask_ms": ph[0] / n_calls * 1e3, "host_policy_ms": ph[1] / n_calls * 1e3,
                 "begin_ms": ph[2] / n_calls * 1e3, "wait_obs_and_expand_ms": ph[3] / n_calls * 1e3}
             return world * N * steps / float(dt.item())
 
         ms_b, ws_b = int(env._b.mask_stride), int(env._L.jss_host_wire_stride(env._h))
-        v_packed = run_e2e(True, args.e2e_steps)
+        run_e2e(True, 8)                                  # first touches: pinned buffers are allocated here, not in a timed run
+        run_e2e(False, 4)
+        # the split between "packed rows + host expansion" and "final fp32 rows by DMA" that balances this box's host
+        # cores against its PCIe link: short calibration runs, then the timed run with the best share
+        calib = {f: run_e2e(True, 12, f) for f in (0.0, 0.15, 0.25, 0.35, 0.5)}
+        if world > 1:                                     # every rank must pick the same share
+            t = torch.tensor([calib[f] for f in sorted(calib)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            calib = dict(zip(sorted(calib), t.tolist()))
+        f_best = max(calib, key=calib.get)
+        phase.clear()
+        v_packed = run_e2e(True, args.e2e_steps, f_best)
         v_plain = run_e2e(False, max(10, args.e2e_steps // 4))
+        n_dma = (int(f_best * N) // 256 * 256) if f_best > 0 else 0
         e2e = {"value": v_packed, "unit": UNIT,
                "h2d_bytes_per_step": 4 * N,
-               "d2h_bytes_per_step": N * ms_b + N * ws_b + 16 * N,
+               "d2h_bytes_per_step": N * ms_b + (N - n_dma) * ws_b + n_dma * J * 7 * 4 + 16 * N,
+               "dma_fraction": f_best, "dma_fraction_calibration": {str(k): v for k, v in calib.items()},
                "steps": args.e2e_steps, "host_threads": threads, "numa_bound_cpus": bound,
                "fp32_dma_variant": {"value": v_plain, "d2h_bytes_per_step": N * ms_b + N * J * 7 * 4 + 16 * N},
                "host_ms_per_step": phase,
-               "note": "jss_host_step_begin_packed / jss_host_wait / jss_host_expand_obs (pinned host buffers): H2D actions, step "
-                       "kernel, D2H mask + scalar records + packed integer observation rows (10 B per job) every step, expansion "
-                       "to the exact fp32 (N, J, 7) observation by the host pool and the host masked-random policy inside the "
-                       "timed region; fp32_dma_variant = the same with 28 B per job of fp32 real_obs over PCIe"}
+               "note": "jss_host_step_begin_hybrid / jss_host_wait / jss_host_expand_obs_range (pinned host buffers): H2D actions, "
+                       "step kernel, D2H mask + scalar records every step; the observation of a share `dma_fraction` of the envs "
+                       "crosses PCIe as final fp32 rows, the rest as packed integer rows (10 B per job) that the host pool expands "
+                       "to the exact fp32 (N, J, 7) observation; expansion and the host masked-random policy are inside the timed "
+                       "region; fp32_dma_variant = everything as 28 B per job of fp32 real_obs over PCIe (the round-1 path)"}
     env.close()
     del env
 

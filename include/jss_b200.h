@@ -227,6 +227,7 @@ int jss_step_host(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, flo
 #define JSS_WAIT_MASK 1
 #define JSS_WAIT_OBS 2       /* observation of the latest begin */
 #define JSS_WAIT_OBS_PREV 3  /* observation of the begin before the latest one */
+#define JSS_WAIT_WIRE 4      /* packed rows of the latest begin (they precede its fp32 rows on the copy stream) */
 int jss_host_step_begin(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, float *obs_host,
                         int32_t *scalars_host, void *after_stream);
 int jss_host_wait(jss_t *h, int what);
@@ -240,6 +241,13 @@ int jss_host_wait(jss_t *h, int what);
  * current_time_step from it).  Waiting works as for jss_host_step_begin: JSS_WAIT_OBS* = the wire rows have landed. */
 int jss_host_step_begin_packed(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, uint8_t *wire_host,
                                int32_t *scalars_host, void *after_stream);
+/* Hybrid: the first n_dma envs ship their observation as final fp32 rows by DMA (obs_host rows [0, n_dma)), the rest as
+ * packed rows (wire_host rows [n_dma, N)) to be expanded with jss_host_expand_obs_range(.., n_dma, N) -- PCIe and the
+ * host cores work in parallel, each on its share.  obs_host: pinned [N][J][7] fp32 (also the expansion target). */
+int jss_host_step_begin_hybrid(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, uint8_t *wire_host,
+                               float *obs_host, int n_dma, int32_t *scalars_host, void *after_stream);
+int jss_host_expand_obs_range(jss_t *h, const uint8_t *wire_host, const int32_t *scalars_host, float *obs_host,
+                              int env_begin, int env_end);
 int64_t jss_host_wire_stride(jss_t *h);
 /* wire rows + scalar records of one step -> obs_host [N][J][7] fp32 (rows of env i: J_i * 7 floats written). */
 int jss_host_expand_obs(jss_t *h, const uint8_t *wire_host, const int32_t *scalars_host, float *obs_host);

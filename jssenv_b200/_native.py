@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "jss_get_buffers", "jss_instance_scalars", "jss_reset", "jss_step", "jss_policy", "jss_rollout",
     "jss_step_host", "jss_host_step_begin", "jss_host_wait", "jss_step_sample", "jss_stats", "jss_export_state", "jss_import_state", "jss_host_masked_random",
     "jss_launch_count", "jss_set_cr_due_date_factor", "jss_host_step_begin_packed", "jss_host_wire_stride",
-    "jss_host_expand_obs", "jss_host_configure", "jss_host_threads", "jss_host_set_simd", "jss_rollout_traj", "jss_step_export",
+    "jss_host_expand_obs", "jss_host_configure", "jss_host_threads", "jss_host_set_simd", "jss_rollout_traj", "jss_step_export", "jss_host_step_begin_hybrid", "jss_host_expand_obs_range",
 )
 
 
@@ -71,6 +71,10 @@ def _declare(L):
     L.jss_host_wait.argtypes = [c_void_p, c_int]
     L.jss_host_step_begin_packed.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.jss_host_step_begin_packed.restype = c_int
+    L.jss_host_step_begin_hybrid.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+    L.jss_host_step_begin_hybrid.restype = c_int
+    L.jss_host_expand_obs_range.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]
+    L.jss_host_expand_obs_range.restype = c_int
     L.jss_host_wire_stride.argtypes = [c_void_p]
     L.jss_host_wire_stride.restype = c_int64
     L.jss_host_expand_obs.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]

@@ -72,14 +72,14 @@ struct jss_handle {
     int32_t *mirror_actions = nullptr;
     JssInstDesc *d_inst = nullptr;
     uint16_t *d_ops = nullptr, *d_rem = nullptr;
-    uint8_t *d_pos = nullptr;
     int32_t *d_len = nullptr;
     unsigned long long *d_stats = nullptr;
 
     JssParams p{};
     JssSmemLayout sl_env{}, sl_step{};               // shared-memory layouts of the generic / step kernels
     int class_tile_begin[3] = {0, 0, 0}, class_tile_end[3] = {0, 0, 0};  // KJ = 1, 2, 4
-    int step_grid[16] = {0};                        // resident-CTA grids of the step kernel variants (filled lazily)
+    int step_grid[16] = {0};
+    int env_grid[12] = {0};                         // resident CTAs per SM of the generic kernel variants (filled lazily)                        // resident-CTA grids of the step kernel variants (filled lazily)
     bool use_pdl = true;
     std::vector<int32_t> env_inst;
 
@@ -89,7 +89,7 @@ struct jss_handle {
     uint8_t *wire[2] = {nullptr, nullptr};         // packed mode: two alternating device rows buffers [N][wire_stride]
     int64_t wire_stride = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
-    cudaEvent_t ev_mask = nullptr, ev_staged = nullptr, ev_obs[2] = {nullptr, nullptr};
+    cudaEvent_t ev_mask = nullptr, ev_staged = nullptr, ev_wire = nullptr, ev_obs[2] = {nullptr, nullptr};
     int pipe_cur = 0;                              // which ev_obs belongs to the latest begin
     bool pipe_ready = false;
 };
@@ -136,7 +136,6 @@ void fill_uni(const JssInstDesc &d, SmInst &u) {
     u.f_mto = (float)d.max_time_op; u.f_mtj = (float)d.max_time_jobs; u.f_sop = (float)d.sum_op; u.f_M = (float)d.M;
     u.r_mto = d.r_mto; u.r_mtj = d.r_mtj; u.r_sop = d.r_sop; u.r_M = d.r_M;
     u.Jcap = round_up(d.J, 4); u.Mcap = round_up(d.M, 4); u.block_words = 5 * u.Jcap + u.Mcap + 12;
-    u.perm = d.perm;
     u.y14[0] = u.y14[1] = u.f_mto; u.r14[0] = u.r14[1] = d.r_mto;
     u.y23[0] = u.f_M; u.y23[1] = u.f_mtj; u.r23[0] = d.r_M; u.r23[1] = d.r_mtj;
     u.y56[0] = u.y56[1] = u.f_sop; u.r56[0] = u.r56[1] = d.r_sop;
@@ -228,9 +227,14 @@ int launch_variant(jss_t *h, const JssLaunch &a, const JssSmemLayout &sl, cudaSt
     const int n_tiles = a.tile_end - a.tile_begin;
     const size_t smem = smem_bytes(sl);
     auto kern = jss_env_kernel<KJ, MODE>;
-    int per_sm = 0;
-    JSS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, JSS_WARPS_PER_CTA * 32, smem));
-    if (per_sm < 1) return fail(h, JSS_ERR_CUDA, "kernel does not fit on an SM (smem %zu B)", smem);
+    // once per handle and kernel variant: opt-in to > 48 KB of dynamic shared memory, resident CTAs per SM
+    int &per_sm = h->env_grid[(KJ == 1 ? 0 : (KJ == 2 ? 1 : 2)) * 4 + (MODE == JSS_MODE_RESET ? 0 : MODE == JSS_MODE_ROLLOUT ? 1 : 2)];
+    if (per_sm == 0) {
+        if (smem > 48 * 1024)
+            JSS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        JSS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, JSS_WARPS_PER_CTA * 32, smem));
+        if (per_sm < 1) { per_sm = 0; return fail(h, JSS_ERR_CUDA, "kernel does not fit on an SM (smem %zu B)", smem); }
+    }
     // policy kernels touch ~50 B per env: latency-bound, so give every tile its own CTA
     // instead of a persistent loop with a dependent load per iteration
     const int grid = (MODE == JSS_MODE_POLICY) ? n_tiles : std::min(n_tiles, h->sm_count * per_sm);
@@ -326,7 +330,7 @@ void jss_destroy(jss_t *h) {
     cudaSetDevice(h->device);
     if (h->pipe_ready) {
         cudaStreamSynchronize(h->s_compute); cudaStreamSynchronize(h->s_copy);
-        cudaEventDestroy(h->ev_mask); cudaEventDestroy(h->ev_staged); cudaEventDestroy(h->ev_obs[0]); cudaEventDestroy(h->ev_obs[1]);
+        cudaEventDestroy(h->ev_mask); cudaEventDestroy(h->ev_staged); cudaEventDestroy(h->ev_wire); cudaEventDestroy(h->ev_obs[0]); cudaEventDestroy(h->ev_obs[1]);
         cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy);
     }
     for (void *ptr : h->allocs) cudaFree(ptr);
@@ -342,7 +346,6 @@ int jss_load_instances(jss_t *h, int n_inst, const int32_t *jobs, const int32_t 
     if (n_inst >= (1 << 23)) return fail(h, JSS_ERR_UNSUPPORTED, "too many instances");
     JSS_CUDA(h, cudaSetDevice(h->device));
     std::vector<uint16_t> ops, rem;
-    std::vector<uint8_t> pos;
     std::vector<int32_t> len;
     h->insts.resize(n_inst);
     h->descs.resize(n_inst);
@@ -360,9 +363,6 @@ int jss_load_instances(jss_t *h, int n_inst, const int32_t *jobs, const int32_t 
         d.ops_off = (int32_t)ops.size();
         d.len_off = (int32_t)len.size();
         d.rem_off = (int32_t)rem.size();
-        d.pos_off = (int32_t)pos.size();
-        d.perm = 1;
-        pos.resize(pos.size() + round_up(J * M, 16), 0);
         ops.resize(ops.size() + round_up(J * M, 8), 0);
         len.resize(len.size() + round_up(J, 4), 0);
         rem.resize(rem.size() + round_up(J * (M + 1), 8), 0);
@@ -384,14 +384,6 @@ int jss_load_instances(jss_t *h, int n_inst, const int32_t *jobs, const int32_t 
             hi.len[j] = (int32_t)total;
             hi.sum_op += total;                                         // jss_env.py:88
             hi.max_time_jobs = std::max(hi.max_time_jobs, total);       // jss_env.py:89
-            {   // machine -> op index; a job that repeats / skips a machine makes the instance "general"
-                std::vector<int> seen((size_t)M, -1);
-                for (int i = 0; i < M; i++) {
-                    if (seen[mm[j * M + i]] >= 0) d.perm = 0;
-                    seen[mm[j * M + i]] = i;
-                }
-                for (int m = 0; m < M; m++) pos[d.pos_off + j * M + m] = (uint8_t)std::max(seen[m], 0);
-            }
             int64_t suffix = 0;
             rem[d.rem_off + j * (M + 1) + M] = 0;
             for (int i = M - 1; i >= 0; i--) {
@@ -414,8 +406,6 @@ int jss_load_instances(jss_t *h, int n_inst, const int32_t *jobs, const int32_t 
     if ((rc = dev_alloc(h, &h->d_ops, ops.size()))) return rc;
     if ((rc = dev_alloc(h, &h->d_len, len.size()))) return rc;
     if ((rc = dev_alloc(h, &h->d_rem, rem.size()))) return rc;
-    if ((rc = dev_alloc(h, &h->d_pos, pos.size()))) return rc;
-    JSS_CUDA(h, cudaMemcpy(h->d_pos, pos.data(), pos.size(), cudaMemcpyHostToDevice));
     JSS_CUDA(h, cudaMemcpy(h->d_inst, h->descs.data(), sizeof(JssInstDesc) * n_inst, cudaMemcpyHostToDevice));
     JSS_CUDA(h, cudaMemcpy(h->d_ops, ops.data(), ops.size() * 2, cudaMemcpyHostToDevice));
     JSS_CUDA(h, cudaMemcpy(h->d_len, len.data(), len.size() * 4, cudaMemcpyHostToDevice));
@@ -551,14 +541,13 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
         for (int e = 0; e < N; e++) uniform = uniform && env_to_inst[e] == env_to_inst[0];
         p.uniform_inst = uniform ? env_to_inst[0] : -1;   // then `order` is the identity (stable sort)
     }
-    p.inst = h->d_inst; p.ops_pool = h->d_ops; p.len_pool = h->d_len; p.rem_pool = h->d_rem; p.pos_pool = h->d_pos;
+    p.inst = h->d_inst; p.ops_pool = h->d_ops; p.len_pool = h->d_len; p.rem_pool = h->d_rem;
 
-    {   // shared-memory layouts: [SmInst][ops u16][len i32][rem u16][pos u8][per-warp regions], 16-byte aligned regions
+    {   // shared-memory layouts: [SmInst][ops u16][len i32][rem u16][per-warp regions], 16-byte aligned regions
         JssSmemLayout sl{};
         sl.off_len = (int32_t)sizeof(SmInst) + round_up(ops_max, 8) * 2;
         sl.off_rem = sl.off_len + round_up(jmax, 4) * 4;
-        sl.off_pos = sl.off_rem + round_up(rem_max, 8) * 2;
-        sl.off_warp0 = sl.off_pos + round_up(ops_max, 16);
+        sl.off_warp0 = sl.off_rem + round_up(rem_max, 8) * 2;
         // observation staging (7 floats per job slot); env_check_no_op (general instances) also keeps its 32-int
         // per-warp machine-horizon table here, so never less than 32 words (tiny instances: 7 * Jcap < 32)
         sl.scratch_words = std::max(7 * p.Jcap, 32);
@@ -774,18 +763,23 @@ int jss_step_host(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, flo
 }
 
 namespace {
+// obs_host != NULL: envs [0, n_dma) ship their observation as fp32 rows by DMA (n_dma < 0: all of them);
+// wire_host != NULL: envs [max(n_dma, 0), N) ship packed integer rows.
 int host_step_begin_impl(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, float *obs_host, uint8_t *wire_host,
-                         int32_t *scalars_host, void *after_stream) {
+                         int32_t *scalars_host, void *after_stream, int n_dma = -1) {
     int rc = check_ready(h);
     if (rc) return rc;
     if (!actions_host) return fail(h, JSS_ERR_INVALID, "jss_host_step_begin: actions_host is NULL");
     const JssParams &p = h->p;
-    const size_t N = (size_t)p.n_envs, obs_bytes = N * p.jobs_max * 7 * 4;
+    const size_t N = (size_t)p.n_envs;
+    const size_t n_fp32 = obs_host ? (n_dma < 0 ? N : std::min<size_t>((size_t)n_dma, N)) : 0;     // envs [0, n_fp32): fp32 by DMA
+    const size_t obs_bytes = n_fp32 * p.jobs_max * 7 * 4;
     if (!h->pipe_ready) {
         JSS_CUDA(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
         JSS_CUDA(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
         JSS_CUDA(h, cudaEventCreateWithFlags(&h->ev_mask, cudaEventDisableTiming));
         JSS_CUDA(h, cudaEventCreateWithFlags(&h->ev_staged, cudaEventDisableTiming));
+        JSS_CUDA(h, cudaEventCreateWithFlags(&h->ev_wire, cudaEventDisableTiming));
         for (int k = 0; k < 2; k++) {
             JSS_CUDA(h, cudaEventCreateWithFlags(&h->ev_obs[k], cudaEventDisableTiming));
             JSS_CUDA(h, cudaEventRecord(h->ev_obs[k], h->s_copy));
@@ -827,12 +821,13 @@ int host_step_begin_impl(jss_t *h, const int32_t *actions_host, uint8_t *mask_ho
     JSS_CUDA(h, cudaEventRecord(h->ev_mask, sc));
     const int prev = h->pipe_cur;
     h->pipe_cur ^= 1;
-    if (obs_host) {
+    if (obs_bytes) {
         // observation: device-side staging copy (so the next step may overwrite real_obs), then the
         // 2.9 KB/env PCIe transfer on its own stream, overlapping the host policy and the next launch
         JSS_CUDA(h, cudaStreamWaitEvent(sc, h->ev_obs[prev], 0));      // previous D2H has drained the staging copy
         JSS_CUDA(h, cudaMemcpyAsync(h->obs_staging, p.obs, obs_bytes, cudaMemcpyDeviceToDevice, sc));
-    } else if (wire_host) {
+    }
+    if (wire_host && n_fp32 < N) {
         // packed rows: 10 bytes per job instead of 28; two device buffers alternate, so this pack only has to wait
         // for the D2H that read the same buffer two begins ago
         JSS_CUDA(h, cudaStreamWaitEvent(sc, h->ev_obs[h->pipe_cur], 0));
@@ -846,11 +841,14 @@ int host_step_begin_impl(jss_t *h, const int32_t *actions_host, uint8_t *mask_ho
     // callers take before going back to the stream-ordered entry points)
     JSS_CUDA(h, cudaEventRecord(h->ev_staged, sc));
     JSS_CUDA(h, cudaStreamWaitEvent(h->s_copy, h->ev_staged, 0));
-    if (obs_host)
+    if (wire_host && n_fp32 < N) {       // the packed rows first: the host has to expand them, the fp32 rows are final
+        const size_t off = n_fp32 * (size_t)h->wire_stride;
+        JSS_CUDA(h, cudaMemcpyAsync(wire_host + off, h->wire[h->pipe_cur] + off, (N - n_fp32) * (size_t)h->wire_stride,
+                                    cudaMemcpyDeviceToHost, h->s_copy));
+        JSS_CUDA(h, cudaEventRecord(h->ev_wire, h->s_copy));
+    }
+    if (obs_bytes)
         JSS_CUDA(h, cudaMemcpyAsync(obs_host, h->obs_staging, obs_bytes, cudaMemcpyDeviceToHost, h->s_copy));
-    else if (wire_host)
-        JSS_CUDA(h, cudaMemcpyAsync(wire_host, h->wire[h->pipe_cur], N * (size_t)h->wire_stride, cudaMemcpyDeviceToHost,
-                                    h->s_copy));
     JSS_CUDA(h, cudaEventRecord(h->ev_obs[h->pipe_cur], h->s_copy));
     return JSS_OK;
 }
@@ -868,20 +866,33 @@ int jss_host_step_begin_packed(jss_t *h, const int32_t *actions_host, uint8_t *m
     return host_step_begin_impl(h, actions_host, mask_host, nullptr, wire_host, scalars_host, after_stream);
 }
 
+int jss_host_step_begin_hybrid(jss_t *h, const int32_t *actions_host, uint8_t *mask_host, uint8_t *wire_host,
+                               float *obs_host, int n_dma, int32_t *scalars_host, void *after_stream) {
+    if (!wire_host || !obs_host || !scalars_host || n_dma < 0)
+        return fail(h, JSS_ERR_INVALID, "jss_host_step_begin_hybrid: wire_host, obs_host, scalars_host and n_dma >= 0 are required");
+    return host_step_begin_impl(h, actions_host, mask_host, obs_host, wire_host, scalars_host, after_stream, n_dma);
+}
+
 int64_t jss_host_wire_stride(jss_t *h) {
     if (!h || !h->assigned) return JSS_ERR_STATE;
     return round_up(JSS_WIRE_JOB_BYTES * h->p.jobs_max + 6, 16);
 }
 
 int jss_host_expand_obs(jss_t *h, const uint8_t *wire_host, const int32_t *scalars_host, float *obs_host) {
+    return jss_host_expand_obs_range(h, wire_host, scalars_host, obs_host, 0, h ? h->n_envs : 0);
+}
+
+int jss_host_expand_obs_range(jss_t *h, const uint8_t *wire_host, const int32_t *scalars_host, float *obs_host,
+                              int env_begin, int env_end) {
     if (!h || !h->assigned) return fail(h, JSS_ERR_STATE, "jss_host_expand_obs: jss_assign must be called first");
-    if (!wire_host || !scalars_host || !obs_host) return fail(h, JSS_ERR_INVALID, "jss_host_expand_obs: NULL buffer");
+    if (!wire_host || !scalars_host || !obs_host || env_begin < 0 || env_end > h->n_envs || env_begin > env_end)
+        return fail(h, JSS_ERR_INVALID, "jss_host_expand_obs: bad arguments");
     std::vector<JssHostInst> hi(h->insts.size());
     for (size_t k = 0; k < h->insts.size(); k++)
         hi[k] = JssHostInst{h->insts[k].J, h->insts[k].M, h->insts[k].max_time_op, h->insts[k].max_time_jobs,
                             h->insts[k].sum_op, h->insts[k].len.data()};
     JssHostExpandArgs a{wire_host, jss_host_wire_stride(h), scalars_host, h->env_inst.data(), hi.data(), obs_host,
-                        h->p.jobs_max, 0, h->n_envs};
+                        h->p.jobs_max, env_begin, env_end};
     jss_host_expand_impl(&a);
     return JSS_OK;
 }
@@ -936,6 +947,7 @@ int jss_host_wait(jss_t *h, int what) {
     if (what == JSS_WAIT_MASK) JSS_CUDA(h, cudaEventSynchronize(h->ev_mask));
     else if (what == JSS_WAIT_OBS) JSS_CUDA(h, cudaEventSynchronize(h->ev_obs[h->pipe_cur]));
     else if (what == JSS_WAIT_OBS_PREV) JSS_CUDA(h, cudaEventSynchronize(h->ev_obs[h->pipe_cur ^ 1]));
+    else if (what == JSS_WAIT_WIRE) JSS_CUDA(h, cudaEventSynchronize(h->ev_wire));
     else return fail(h, JSS_ERR_INVALID, "jss_host_wait: unknown selector %d", what);
     return JSS_OK;
 }

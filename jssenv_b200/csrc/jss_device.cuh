@@ -41,7 +41,6 @@ struct InstView {  // instance tables staged in shared memory
     const uint16_t *ops;
     const int32_t *len;
     const uint16_t *rem;
-    const uint8_t *pos;
     const SmInst *si;
 };
 
@@ -426,43 +425,6 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
         }
     }
     const int last = iv.si->M - 1;
-    if (iv.si->perm) {
-        // Permutation instance (every job visits every machine exactly once): the walk of pass 2 (:324-401) can be
-        // answered per legal machine in closed form.  A job that starts walking at op ts0 and time tm0 reaches its
-        // op on machine m -- op index k = pos[j][m] -- at  tm0 + sum(dur[ts0 .. k-1]) = tm0 + rem[ts0] - rem[k]  (suffix
-        // sums), provided ts0 <= k < M-1; the walk's stop test `max_horizon > time` cannot fire before that because
-        // max_horizon >= the horizon of every legal machine (it is the running maximum of their prefix minima) and
-        // times only grow along the walk.  So machine m joins machine_next (:351 / :391) iff its horizon lies beyond
-        // that arrival time: branch-free, at most 3 legal machines, no divergent per-lane loops.
-        uint32_t want = 0u;
-#pragma unroll
-        for (int i = 0; i < KJ; i++) {
-            const int tq = __shfl_sync(JSS_FULL, s.tuam, (int)(jss_op_m(s.op[i]) & 31u));   // countdown of the job's machine
-            const bool running = s.tufco[i] > 0;
-            // walkers: jobs that are not legal and either running (case 1, :327-337) or idle and not blocked by a
-            // no-op (case 2, :366-377); finished / padding slots (todo == M) never walk
-            const bool walker = !(s.lb & (1u << i)) && s.todo[i] < iv.si->M && (running || !(s.lb & (16u << i)));
-            const int ts0 = s.todo[i] + (running ? 1 : 0);
-            const int tm0 = s.t + (running ? s.tufco[i] : tq);
-            const int j = min(KJ * lane + i, iv.si->J - 1);
-            const uint16_t *rem_j = iv.rem + j * (iv.si->M + 1);
-            const uint8_t *pos_j = iv.pos + j * iv.si->M;
-            const int base = tm0 + (int)rem_j[min(ts0, iv.si->M)];
-#define JSS_NOOP_PROBE(LM, H)                                                                           \
-            if (LM >= 0) {                               /* warp-uniform */                             \
-                const int k = (int)pos_j[LM];                                                           \
-                const int arrive = base - (int)rem_j[k];                                                \
-                want |= (uint32_t)(walker && k >= ts0 && k < last && H > arrive) << LM;                 \
-            }
-            JSS_NOOP_PROBE(lm0, h0)
-            JSS_NOOP_PROBE(lm1, h1)
-            JSS_NOOP_PROBE(lm2, h2)
-#undef JSS_NOOP_PROBE
-        }
-        want = __reduce_or_sync(JSS_FULL, want);
-        return ML != 0u && want == ML;                  // len(machine_next) == nb_machine_legal
-    }
-    // general instance (a job may visit a machine twice / never): literal walks.
     // per-machine horizon table: finite only for machines that have a legal job, so the
     // walk's test `max_horizon_machine[m] > time and machine_legal[m]` is one compare
     hz[lane] = (lane == lm0) ? h0 : (lane == lm1) ? h1 : (lane == lm2) ? h2 : (int)0x80000000;
@@ -499,9 +461,18 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
     return ML != 0u && want == ML;                      // len(machine_next) == nb_machine_legal
 }
 
+// Output bases of the emit helpers: the library's per-env buffers by default, the caller's trajectory buffers when a
+// rollout records (then `env` is the trajectory slot k * N + env).
+struct JssOut {
+    float *obs;
+    uint8_t *mask;
+    int32_t *scalars;
+};
+JSS_DEV JssOut jss_out_default(const JssParams &p) { return JssOut{p.obs, p.mask, p.scalars}; }
+
 // ---- observation / mask / reward (jss_env.py:102-134, 483-493) ---------------------
 template <int KJ, bool BULK = false>
-JSS_DEV void env_emit_obs(const JssParams &p, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane,
+JSS_DEV void env_emit_obs(const JssParams &p, const JssOut &out, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane,
                           float *scratch, jss_saddr_t scratch_sa = jss_saddr_t(), void *st_dst = nullptr,
                           jss_saddr_t st_sa = jss_saddr_t(), uint32_t st_bytes = 0u) {
     if (KJ * lane < iv.si->J) {
@@ -536,7 +507,7 @@ JSS_DEV void env_emit_obs(const JssParams &p, const InstView &iv, const EnvRegs<
             for (int q = 0; q < 7; q++) mine[q] = v[q];
         }
     }
-    float *dst = p.obs + (size_t)env * p.jobs_max * 7;
+    float *dst = out.obs + (size_t)env * p.jobs_max * 7;
     const int n = iv.si->J * 7;
     if (BULK) {
         // ONE proxy fence covers both staged buffers (new state block + observation rows), then lane 0
@@ -565,9 +536,9 @@ JSS_DEV void env_emit_obs(const JssParams &p, const InstView &iv, const EnvRegs<
 }
 
 template <int KJ>
-JSS_DEV void env_emit_mask(const JssParams &p, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane,
+JSS_DEV void env_emit_mask(const JssParams &p, const JssOut &out, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane,
                            bool noop) {
-    uint8_t *row = p.mask + (size_t)env * p.mask_stride;
+    uint8_t *row = out.mask + (size_t)env * p.mask_stride;
     const int j0 = KJ * lane;
     if (j0 <= iv.si->J) {
         // spread the legal bits to bytes: bit i -> byte i
@@ -584,11 +555,11 @@ JSS_DEV void env_emit_mask(const JssParams &p, const InstView &iv, const EnvRegs
 // reward / raw reward / time / (flags << 8 | done) of an env are ONE 16-byte record, so the
 // per-step scalar outputs cost a single store (the API exposes them as strided arrays)
 template <int KJ>
-JSS_DEV void env_emit_scalars(const JssParams &p, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane,
+JSS_DEV void env_emit_scalars(const JssOut &out, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane,
                               int raw_reward) {
     if (lane == 0) {
         const float r = jss_div((float)raw_reward, iv.si->f_mto, iv.si->r_mto);   // :483-493
-        reinterpret_cast<int4 *>(p.scalars)[env] =
+        reinterpret_cast<int4 *>(out.scalars)[env] =
             make_int4(__float_as_int(r), raw_reward, s.t, (int)((s.flags << 8) | (s.flags & JSS_FLAG_DONE)));
     }
 }
@@ -840,8 +811,8 @@ JSS_DEV void env_pack(const JssLaunch &a, const InstView &iv, const EnvRegs<KJ> 
 // ---- CTA-level driver -----------------------------------------------------------------------
 struct JssSmemLayout {
     // byte offsets from the start of dynamic shared memory, precomputed on the host so the kernels derive every
-    // pointer with one add (each region 16-byte aligned): [SmInst][ops u16][len i32][rem u16][pos u8][per-warp regions]
-    int32_t off_len, off_rem, off_pos, off_warp0;
+    // pointer with one add (each region 16-byte aligned): [SmInst][ops u16][len i32][rem u16][per-warp regions]
+    int32_t off_len, off_rem, off_warp0, pad0_;
     int32_t warp_stride;    // bytes per warp region
     int32_t scratch_words;  // observation staging (7 floats per job slot), >= 32 words
     int32_t off_scratch;    // step kernels: [mbarrier 16 B][state-in block][scratch][state-out block]; else 0
@@ -853,21 +824,18 @@ struct JssCtaSmem {         // the CTA-shared part
     uint16_t *ops;
     int32_t *len;
     uint16_t *rem;
-    uint8_t *pos;
 };
 JSS_DEV void jss_cta_carve(const JssSmemLayout &sl, char *sm, JssCtaSmem &c, InstView &iv) {
     c.si = reinterpret_cast<SmInst *>(sm);
     c.ops = reinterpret_cast<uint16_t *>(sm + sizeof(SmInst));
     c.len = reinterpret_cast<int32_t *>(sm + sl.off_len);
     c.rem = reinterpret_cast<uint16_t *>(sm + sl.off_rem);
-    c.pos = reinterpret_cast<uint8_t *>(sm + sl.off_pos);
-    iv.ops = c.ops; iv.len = c.len; iv.rem = c.rem; iv.pos = c.pos; iv.si = c.si;
+    iv.ops = c.ops; iv.len = c.len; iv.rem = c.rem; iv.si = c.si;
 }
 
 #define JSS_STAGE_OPS 1     // ops + jobs_length
-#define JSS_STAGE_REM 2     // suffix sums (rules MWR / LWR / CR, _check_no_op on permutation instances)
-#define JSS_STAGE_POS 4     // machine -> op index (_check_no_op on permutation instances)
-#define JSS_STAGE_ALL 7
+#define JSS_STAGE_REM 2     // suffix sums (rules MWR / LWR / CR)
+#define JSS_STAGE_ALL 3
 
 JSS_DEV void jss_fill_sminst(const JssInstDesc &d, SmInst *si) {
     si->J = d.J; si->M = d.M; si->max_time_op = d.max_time_op; si->max_time_jobs = d.max_time_jobs;
@@ -876,7 +844,6 @@ JSS_DEV void jss_fill_sminst(const JssInstDesc &d, SmInst *si) {
     si->f_M = (float)d.M;
     si->r_mto = d.r_mto; si->r_mtj = d.r_mtj; si->r_sop = d.r_sop; si->r_M = d.r_M;
     si->Jcap = (d.J + 3) & ~3; si->Mcap = (d.M + 3) & ~3; si->block_words = 5 * si->Jcap + si->Mcap + 12;
-    si->perm = d.perm;
     si->y14[0] = si->y14[1] = si->f_mto; si->r14[0] = si->r14[1] = d.r_mto;
     si->y23[0] = si->f_M; si->y23[1] = si->f_mtj; si->r23[0] = d.r_M; si->r23[1] = d.r_mtj;
     si->y56[0] = si->y56[1] = si->f_sop; si->r56[0] = si->r56[1] = d.r_sop;
@@ -906,21 +873,16 @@ JSS_DEV void jss_stage_instance(const JssParams &p, const JssInstDesc &d, const 
         const int n = (d.J * (d.M + 1) + 7) >> 3;
         for (int k = tid; k < n; k += nt) dst[k] = src[k];
     }
-    if ((what & JSS_STAGE_POS) && d.perm) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.pos_pool + d.pos_off);
-        uint4 *dst = reinterpret_cast<uint4 *>(c.pos);
-        const int n = (d.J * d.M + 15) >> 4;
-        for (int k = tid; k < n; k += nt) dst[k] = src[k];
-    }
 }
 
 template <int KJ, bool BULK = false>
 JSS_DEV void env_emit_all(const JssParams &p, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane,
                           float *scratch, int raw, jss_saddr_t scratch_sa = jss_saddr_t(), void *st_dst = nullptr,
                           jss_saddr_t st_sa = jss_saddr_t(), uint32_t st_bytes = 0u) {
-    env_emit_obs<KJ, BULK>(p, iv, s, env, lane, scratch, scratch_sa, st_dst, st_sa, st_bytes);
-    env_emit_mask<KJ>(p, iv, s, env, lane, (s.flags & JSS_FLAG_NOOP_LEGAL) != 0u);
-    env_emit_scalars<KJ>(p, iv, s, env, lane, raw);
+    const JssOut out = jss_out_default(p);
+    env_emit_obs<KJ, BULK>(p, out, iv, s, env, lane, scratch, scratch_sa, st_dst, st_sa, st_bytes);
+    env_emit_mask<KJ>(p, out, iv, s, env, lane, (s.flags & JSS_FLAG_NOOP_LEGAL) != 0u);
+    env_emit_scalars<KJ>(out, iv, s, env, lane, raw);
 }
 
 template <int KJ, int MODE>
@@ -947,8 +909,8 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
         env_import<KJ>(p, iv, s, env, lane);
         s.ep_steps = 0; s.ep_return = 0;
         env_store<KJ>(p, iv, env, lane, s);
-        env_emit_obs<KJ>(p, iv, s, env, lane, scratch);
-        env_emit_mask<KJ>(p, iv, s, env, lane, (s.flags & JSS_FLAG_NOOP_LEGAL) != 0u);
+        env_emit_obs<KJ>(p, jss_out_default(p), iv, s, env, lane, scratch);
+        env_emit_mask<KJ>(p, jss_out_default(p), iv, s, env, lane, (s.flags & JSS_FLAG_NOOP_LEGAL) != 0u);
         if (lane == 0) p.scalars[4 * (size_t)env + 3] = (int32_t)((s.flags << 8) | (s.flags & JSS_FLAG_DONE));
         return;
     }
@@ -988,8 +950,7 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
         // trajectory recording: step k of this env writes its observation / mask / scalar record (and the action that
         // led to it) into slot k * n_envs + env of the caller's [n_steps][N][...] buffers -- the emit helpers index
         // their outputs by env only, so a shifted index is all it takes
-        JssParams pt = p;
-        pt.obs = a.traj_obs; pt.mask = a.traj_mask; pt.scalars = a.traj_scalars;
+        const JssOut traj{a.traj_obs, a.traj_mask, a.traj_scalars};
         for (int k = 0; k < a.n_steps; k++) {
             const uint32_t h = jss_hash3(a.seed, genv, a.step_index + (uint64_t)k);
             const int act = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
@@ -998,7 +959,9 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
             if (changed) { raw = r; dirty = true; }
             const int slot = k * p.n_envs + env;
             if (a.traj_actions && lane == 0) a.traj_actions[slot] = act;
-            env_emit_all<KJ>(pt, iv, s, slot, lane, scratch, changed ? r : 0);
+            env_emit_obs<KJ>(p, traj, iv, s, slot, lane, scratch);
+            env_emit_mask<KJ>(p, traj, iv, s, slot, lane, (s.flags & JSS_FLAG_NOOP_LEGAL) != 0u);
+            env_emit_scalars<KJ>(traj, iv, s, slot, lane, changed ? r : 0);
         }
     } else {
         for (int k = 0; k < a.n_steps; k++) {
@@ -1033,8 +996,8 @@ JSS_DEV void jss_tile_desc(const JssParams &p, int tile, int &first, int &inst, 
 #define JSS_MIN_CTAS 3   // 78 registers, no spills -> 3 CTAs = 24 warps per SM (sweeps in profiles/)
 #endif
 #ifndef JSS_MIN_CTAS_SMALL
-#define JSS_MIN_CTAS_SMALL JSS_MIN_CTAS   // uniform batches with <= 64 jobs (KJ = 1, 2): latency-bound, may want more warps
-#endif
+#define JSS_MIN_CTAS_SMALL 4   // uniform batches with <= 32 jobs (KJ = 1) are latency-bound: 4 CTAs = 32 warps per SM at 64 registers
+#endif                         // (measured: 15x15 .. 30x20 shapes -4 %, ta01 N = 4096 8.1 -> 6.7 us per step; no gain for KJ = 2)
 
 template <int KJ, int MODE>
 __global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, 1)
@@ -1049,7 +1012,7 @@ jss_env_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     // what the mode reads: the masked-uniform sampler looks at no instance table at all (only J); the other policies
     // at ops / len (+ suffix sums for MWR / LWR / CR); everything that steps needs all tables
     int what = JSS_STAGE_OPS;
-    if (MODE == JSS_MODE_ROLLOUT || a.mode == JSS_MODE_STEP) what = JSS_STAGE_ALL;
+    if (MODE == JSS_MODE_ROLLOUT) what = JSS_STAGE_ALL;
     if (MODE == JSS_MODE_POLICY)
         what = a.rule == JSS_RULE_RANDOM ? 0
              : (a.rule == JSS_RULE_MWR || a.rule == JSS_RULE_LWR || a.rule == JSS_RULE_CR) ? (JSS_STAGE_OPS | JSS_STAGE_REM)
@@ -1147,7 +1110,7 @@ JSS_DEV void jss_step_tiles(const JssParams &p, const JssLaunch &a, const JssSme
             const int inst = p.tiles[tile].inst_count >> 8;
             if (inst != staged) {                        // CTA-uniform
                 __syncthreads();
-                jss_stage_instance(p, p.inst[inst], c, JSS_STAGE_ALL);
+                jss_stage_instance(p, p.inst[inst], c, (SAMPLE == 2 && a.rule >= JSS_RULE_MWR) ? JSS_STAGE_ALL : JSS_STAGE_OPS);
                 staged = inst;
                 __syncthreads();
             }
@@ -1212,7 +1175,7 @@ JSS_DEV void jss_step_carve(const JssSmemLayout &sl, char *sm, int warp, JssWarp
 // Uniform batch (every env runs the same instance): static strided tiles, the per-instance scalars are
 // read from the kernel parameters (constant-bank operands), no CTA barrier after the first staging.
 template <int KJ, int SAMPLE>
-__global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, KJ == 4 ? JSS_MIN_CTAS : JSS_MIN_CTAS_SMALL)
+__global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, KJ == 1 ? JSS_MIN_CTAS_SMALL : JSS_MIN_CTAS)
 jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JSS_SMEM_DECL(jss_smem);
     char *sm = reinterpret_cast<char *>(jss_smem);
@@ -1226,7 +1189,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     if (lane == 0) jss_mbar_init(w.mbar);
     jss_pdl_launch_dependents();
     // prologue on read-only data (overlaps the tail of the previous launch under PDL)
-    jss_stage_instance(p, p.inst[p.uniform_inst], c, JSS_STAGE_ALL);
+    jss_stage_instance(p, p.inst[p.uniform_inst], c, (SAMPLE == 2 && a.rule >= JSS_RULE_MWR) ? JSS_STAGE_ALL : JSS_STAGE_OPS);
     __syncthreads();
     jss_pdl_wait();
     int staged = p.uniform_inst;

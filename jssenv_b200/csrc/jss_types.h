@@ -5,8 +5,7 @@
 // ---- packed instance tables (read-only, built by jss_load_instances) ----------
 // ops_pool  u16 [J*M]      op = (machine << 11) | duration   (M <= 32, duration <= 2047)
 // len_pool  i32 [J]        jobs_length[j] = sum of durations (jss_env.py:87)
-// rem_pool  u16 [J*(M+1)]  rem[j][k] = sum of durations of ops k..M-1 (rules MWR/LWR/CR; _check_no_op arrival times)
-// pos_pool  u8  [J*M]      pos[j][m] = index of the op of job j that runs on machine m (permutation instances only)
+// rem_pool  u16 [J*(M+1)]  rem[j][k] = sum of durations of ops k..M-1 (rules MWR/LWR/CR)
 #define JSS_OP_SHIFT 11
 #define JSS_OP_DMASK 2047u
 #define JSS_OP_NONE 0xFFFFFFFFu  // register-only marker "job has no current op" (finished / padding): machine field >= 32
@@ -17,8 +16,6 @@ struct JssInstDesc {
     int32_t ops_off;                              // offsets into the pools, in elements
     int32_t len_off;
     int32_t rem_off;
-    int32_t pos_off;
-    int32_t perm;                                 // 1: every job visits every machine exactly once (all bundled instances)
     // correctly rounded fp32 reciprocals of the four observation divisors (jss_div)
     float r_mto, r_mtj, r_sop, r_M;
 };
@@ -64,7 +61,6 @@ struct JssParams {
     const uint16_t *ops_pool;
     const int32_t *len_pool;
     const uint16_t *rem_pool;
-    const uint8_t *pos_pool;
     const int32_t *order;    // env ids grouped by (KJ class, instance)
     const JssTile *tiles;
     const JssCtaRange *cta_ranges;   // mixed-batch step kernel: one equal-cost contiguous tile range per CTA
@@ -93,10 +89,9 @@ struct SmInst {
     float f_mto, f_mtj, f_sop, f_M;       // the divisors as floats ...
     float r_mto, r_mtj, r_sop, r_M;       // ... and their correctly rounded reciprocals
     int Jcap, Mcap, block_words;          // state-block geometry of THIS instance: J, M rounded up to 4; 5*Jcap + Mcap + 12
-    int perm;                             // permutation instance: _check_no_op uses the position / suffix-sum tables
     // divisor / reciprocal PAIRS for the packed (f32x2) observation quotients: columns (1,4), (2,3), (5,6)
     float y14[2], r14[2], y23[2], r23[2], y56[2], r56[2];
-    int pad_[3];                          // 32 words: the tables behind it in shared memory stay 16-byte aligned
+    int pad_[4];                          // 32 words: the tables behind it in shared memory stay 16-byte aligned
 };
 static_assert(sizeof(SmInst) % 16 == 0, "SmInst must keep the shared-memory tables 16-byte aligned");
 struct JssLaunch {           // per-launch arguments

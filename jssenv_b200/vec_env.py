@@ -274,11 +274,13 @@ class JssVecEnv:
         return obs, hv["reward"], hv["done"], np.zeros(n, np.bool_), {}
 
     # pipelined form: begin -> wait_mask -> (choose next actions) -> begin ... ; obs lands in alternating buffers
-    def host_step_begin(self, actions: np.ndarray, packed: bool = False):
+    def host_step_begin(self, actions: np.ndarray, packed: bool = False, dma_fraction: float = 0.0):
         """Enqueue one host-buffer step and return immediately (see jss_host_step_begin).  Results land
         in this call's slot of two alternating pinned buffer sets; use host_wait_mask()/host_wait_obs().
         packed=True ships the observation as 10-byte integer records per job instead of 28 bytes of fp32
-        (jss_host_step_begin_packed); host_wait_obs() then expands them to the exact float observation."""
+        (jss_host_step_begin_packed); host_wait_obs() then expands them to the exact float observation.
+        dma_fraction > 0 (with packed): that share of the envs ships final fp32 rows by DMA instead, so PCIe and the
+        host cores each work on their part in parallel (jss_host_step_begin_hybrid)."""
         a = np.ascontiguousarray(actions, dtype=np.int32)
         n, J = self.num_envs, self.jobs
         if not hasattr(self, "_pipe"):
@@ -287,7 +289,7 @@ class JssVecEnv:
             mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin)   # noqa: E731
             ms = int(self._b.mask_stride)
             ws = int(self._L.jss_host_wire_stride(self._h))
-            self._pipe = [{"mask": mk((n, ms), torch.uint8), "obs": None, "wire": None, "wire_stride": ws,
+            self._pipe = [{"mask": mk((n, ms), torch.uint8), "obs": None, "wire": None, "wire_stride": ws, "n_dma": 0,
                            "scalars": mk((n, 4), torch.int32), "actions": mk((n,), torch.int32), "packed": False,
                            "expanded": True} for _ in range(2)]
             self._pipe_slot = 0
@@ -308,7 +310,17 @@ class JssVecEnv:
         b["actions"].numpy()[:] = a                      # pinned copy: the H2D must not race with the caller's array
         b["packed"] = bool(packed)
         b["expanded"] = not packed
-        if packed:
+        b["n_dma"] = 0
+        if packed and dma_fraction > 0.0:
+            g = 256 if n >= 4096 else 1
+            b["n_dma"] = min(n, int(dma_fraction * n) // g * g)
+        if packed and b["n_dma"] > 0:
+            rc = self._L.jss_host_step_begin_hybrid(self._h, ctypes.c_void_p(b["actions"].data_ptr()),
+                                                    ctypes.c_void_p(b["mask"].data_ptr()),
+                                                    ctypes.c_void_p(b["wire"].data_ptr()),
+                                                    ctypes.c_void_p(b["obs"].data_ptr()), b["n_dma"],
+                                                    ctypes.c_void_p(b["scalars"].data_ptr()), self._stream())
+        elif packed:
             rc = self._L.jss_host_step_begin_packed(self._h, ctypes.c_void_p(b["actions"].data_ptr()),
                                                     ctypes.c_void_p(b["mask"].data_ptr()),
                                                     ctypes.c_void_p(b["wire"].data_ptr()),
@@ -336,8 +348,9 @@ class JssVecEnv:
         N.check(self._h, self._L.jss_host_wait(self._h, N.WAIT_OBS_PREV if previous else N.WAIT_OBS), "jss_host_wait")
         b = self._pipe[self._pipe_slot ^ (1 if previous else 0)]
         if b["packed"] and not b["expanded"]:
-            rc = self._L.jss_host_expand_obs(self._h, ctypes.c_void_p(b["wire"].data_ptr()),
-                                             ctypes.c_void_p(b["scalars"].data_ptr()), ctypes.c_void_p(b["obs"].data_ptr()))
+            rc = self._L.jss_host_expand_obs_range(self._h, ctypes.c_void_p(b["wire"].data_ptr()),
+                                                   ctypes.c_void_p(b["scalars"].data_ptr()),
+                                                   ctypes.c_void_p(b["obs"].data_ptr()), int(b["n_dma"]), self.num_envs)
             N.check(self._h, rc, "jss_host_expand_obs")
             b["expanded"] = True
         return b["obs"].numpy()

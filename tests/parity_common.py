@@ -481,7 +481,9 @@ def check_host_pipeline_packed(make_env, names, seed, n_steps=80):
         assert np.array_equal(rew, _np(ref.reward)) and np.array_equal(done, _np(ref.done))
         nxt = env.host_masked_random(mask, 1000 + k)
         expected = _np(ref.real_obs).copy()
-        env.host_step_begin(nxt, packed=True)          # next step enqueued while the previous rows may still stream
+        # next step enqueued while the previous rows may still stream; every third step ships a share of the envs as
+        # final fp32 rows by DMA (hybrid)
+        env.host_step_begin(nxt, packed=True, dma_fraction=(0.0, 0.0, 0.4)[k % 3] if len(names) >= 4 else 0.0)
         env._L.jss_host_set_simd(k % 3)                # scalar / AVX2 / AVX-512 expansion paths in turn
         got = env.host_wait_obs(previous=True)
         for i, J in enumerate(env.env_jobs):
