@@ -188,12 +188,7 @@ int launch_step_mixed(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStream
     const int slot = 12 + SAMPLE + (want_rem ? 1 : 0);
     int rc = step_grid_for(h, kern, slot, smem);
     if (rc) return rc;
-    const int grid = h->p.n_cta_ranges;                   // one static equal-cost range per CTA (all resident: SMs x 3)
-    {
-        static const bool sm_major = !(getenv("JSS_MIXED_MAP") && getenv("JSS_MIXED_MAP")[0] == '0');
-        const int per_sm = grid / h->sm_count;
-        if (sm_major && per_sm >= 1 && per_sm * h->sm_count == grid) { a.range_sms = h->sm_count; a.range_per_sm = per_sm; }
-    }
+    const int grid = h->p.n_cta_ranges;                   // one CTA per range (all resident: SMs x 3)
     if (h->use_pdl) JSS_CUDA(h, JSS_LAUNCH_PDL(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl));
     else JSS_LAUNCH(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl);
     JSS_CUDA(h, cudaGetLastError());
@@ -496,34 +491,24 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
     if (off16 >= (1ull << 32)) return fail(h, JSS_ERR_UNSUPPORTED, "state exceeds 64 GiB");
     const size_t state_words = (size_t)off16 * 4;
 
-    // mixed-batch step kernel: one contiguous, equal-cost tile range per persistent CTA.  Cost of an env-step as a
-    // function of J, measured on uniform 65 536-env batches (profiles/r02_probe_shapes.json): 0.95 / 0.90 / 0.97 /
-    // 1.17 / 1.41 ns for J = 15 / 20 / 30 / 50 / 100 -- small envs are latency-bound, so the cost is far from
-    // proportional to the bytes they move.
+    // mixed-batch step kernel: every persistent CTA gets an equal slice of EVERY lane class (tile counts differ by at
+    // most one per class; the extras are dithered with a different phase per class so that no CTA collects them all)
     std::vector<JssCtaRange> ranges;
     {
-        double ca = 0.84, cb = 0.0057;
-        if (const char *e = getenv("JSS_COST_A")) ca = atof(e);
-        if (const char *e = getenv("JSS_COST_B")) cb = atof(e);
-        std::vector<double> cum(tiles.size() + 1, 0.0);
-        for (size_t t = 0; t < tiles.size(); t++) {
-            const int k = tiles[t].inst_count >> 8, cnt = tiles[t].inst_count & 255;
-            cum[t + 1] = cum[t] + cnt * (ca + cb * h->insts[k].J);
-        }
         const int n_cta = std::max(1, std::min((int)tiles.size(), h->sm_count * JSS_MIN_CTAS));
-        // tiles are ordered KJ=4 | KJ=2 | KJ=1; ends of the first two groups (empty classes collapse)
-        const int c4e = h->class_tile_end[2] > h->class_tile_begin[2] ? h->class_tile_end[2] : 0;
-        const int c2e = h->class_tile_end[1] > h->class_tile_begin[1] ? h->class_tile_end[1] : c4e;
-        int t = 0;
-        for (int b = 0; b < n_cta; b++) {
-            const double target = cum.back() * (b + 1) / n_cta;
-            int e = t;
-            while (e < (int)tiles.size() && (b == n_cta - 1 || cum[e + 1] <= target + 1e-9)) e++;
-            auto clampi = [&](int v) { return std::min(std::max(v, t), e); };
-            ranges.push_back(JssCtaRange{t, clampi(c4e), clampi(c2e), e});
-            t = e;
+        ranges.resize((size_t)n_cta);
+        for (int c = 0; c < 3; c++) {                     // c = 2: KJ = 4, c = 1: KJ = 2, c = 0: KJ = 1
+            const int tb = h->class_tile_begin[c], n = h->class_tile_end[c] - tb;
+            const int shift = (c * n_cta) / 3;            // CTA that starts this class's Bresenham sequence
+            int given = 0;
+            for (int k = 0; k < n_cta; k++) {
+                const int b = (k + shift) % n_cta;
+                const int upto = (int)(((int64_t)(k + 1) * n) / n_cta);
+                int32_t *lo = c == 2 ? &ranges[b].a4 : (c == 1 ? &ranges[b].a2 : &ranges[b].a1);
+                lo[0] = tb + given; lo[1] = tb + upto;
+                given = upto;
+            }
         }
-        if (t != (int)tiles.size()) return fail(h, JSS_ERR_INVALID, "internal: CTA ranges do not cover the tile list");
     }
 
     JssParams &p = h->p;

@@ -1201,12 +1201,12 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     if (lane == 0) jss_bulk_store_wait_all();            // shared memory must outlive the bulk reads
 }
 
-// Mixed batch: ONE persistent launch covers the three lane classes.  The host splits the (class, instance)-sorted
-// tile list into one contiguous, equal-COST range per CTA (per-class costs measured on uniform batches, see
-// jss_assign); a CTA walks its range class by class -- three complete loops in sequence, so each lane class keeps the
-// register allocation of its stand-alone kernel -- and re-stages instance tables only when the instance changes.
-// Co-resident CTAs work on different classes, which mixes issue-bound (100-job) and latency-bound (15-job) warps
-// on every SM.
+// Mixed batch: ONE persistent launch covers the three lane classes.  Every CTA gets an equal slice of EVERY class
+// (tile counts differ by at most one per class, the extras dithered across CTAs), so the launch is balanced without a
+// cost model, and walks them class by class -- three complete loops in sequence, so each lane class keeps the register
+// allocation of its stand-alone kernel.  All CTAs start with the 100-job class and move on at about the same time:
+// the CTAs that share an SM mostly execute the same 40-60 KB loop body (the three together are 120 KB, more than
+// the instruction cache holds).  Instance tables are re-staged only when the instance changes.
 template <int SAMPLE>
 __global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, JSS_MIN_CTAS)
 jss_step_mixed_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
@@ -1220,19 +1220,14 @@ jss_step_mixed_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout 
     jss_step_carve(sl, sm, warp, w);
     if (lane == 0) jss_mbar_init(w.mbar);
     jss_pdl_launch_dependents();
-    // Which range?  Ranges are consecutive in (class, instance) order, and CTAs b, b + #SMs, b + 2 #SMs normally share
-    // an SM (the block scheduler deals the resident grid out round-robin): giving them CONSECUTIVE ranges makes the
-    // CTAs of one SM run the same lane class, i.e. one 40-60 KB loop body per SM instead of all three (130 KB) fighting
-    // over the instruction cache.  Correctness does not depend on the placement -- it is a fixed permutation.
-    int ridx = (int)blockIdx.x;
-    if (a.range_sms > 0) ridx = ((int)blockIdx.x % a.range_sms) * a.range_per_sm + (int)blockIdx.x / a.range_sms;
-    const int4 r = *reinterpret_cast<const int4 *>(p.cta_ranges + ridx);   // tile cuts: [x,y) KJ=4, [y,z) KJ=2, [z,w) KJ=1
+    const int4 r0 = reinterpret_cast<const int4 *>(p.cta_ranges + blockIdx.x)[0];   // [a4, b4) [a2, b2)
+    const int4 r1 = reinterpret_cast<const int4 *>(p.cta_ranges + blockIdx.x)[1];   // [a1, b1)
     jss_pdl_wait();
     int staged = -1;
     uint32_t phase = 0;
-    jss_step_tiles<4, SAMPLE, false>(p, a, sl, iv, c, w, warp, lane, r.x, r.y, 1, staged, phase);
-    jss_step_tiles<2, SAMPLE, false>(p, a, sl, iv, c, w, warp, lane, r.y, r.z, 1, staged, phase);
-    jss_step_tiles<1, SAMPLE, false>(p, a, sl, iv, c, w, warp, lane, r.z, r.w, 1, staged, phase);
+    jss_step_tiles<4, SAMPLE, false>(p, a, sl, iv, c, w, warp, lane, r0.x, r0.y, 1, staged, phase);
+    jss_step_tiles<2, SAMPLE, false>(p, a, sl, iv, c, w, warp, lane, r0.z, r0.w, 1, staged, phase);
+    jss_step_tiles<1, SAMPLE, false>(p, a, sl, iv, c, w, warp, lane, r1.x, r1.y, 1, staged, phase);
     if (lane == 0) jss_bulk_store_wait_all();            // shared memory must outlive the bulk reads
 }
 

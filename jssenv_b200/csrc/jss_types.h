@@ -48,8 +48,9 @@ struct JssTile {       // one CTA work item: up to `count` envs of ONE instance 
     uint32_t block16;  // block size of this tile's instance in 16-byte units
 };
 
-struct JssCtaRange {   // mixed batches: the tiles of one persistent CTA, cut at the lane-class boundaries
-    int32_t t4, t2, t1, tend;   // [t4, t2) KJ = 4 tiles, [t2, t1) KJ = 2, [t1, tend) KJ = 1
+struct JssCtaRange {   // mixed batches: the tiles of one persistent CTA -- an equal slice of EVERY lane class
+    int32_t a4, b4, a2, b2;     // [a4, b4) KJ = 4 tiles, [a2, b2) KJ = 2 tiles,
+    int32_t a1, b1, pad_[2];    // [a1, b1) KJ = 1 tiles
 };
 
 struct JssParams {
@@ -63,7 +64,7 @@ struct JssParams {
     const uint16_t *rem_pool;
     const int32_t *order;    // env ids grouped by (KJ class, instance)
     const JssTile *tiles;
-    const JssCtaRange *cta_ranges;   // mixed-batch step kernel: one equal-cost contiguous tile range per CTA
+    const JssCtaRange *cta_ranges;   // mixed-batch step kernel: per CTA an equal slice of every lane class
     int32_t n_cta_ranges;
     const uint32_t *state_off16;   // per env: start of its state block, in 16-byte units (tile order, see JssTile)
     const uint32_t *hdr_off16;     // per env: start of its 4-word header (t, flags, episode steps / return), 16-byte units
@@ -98,7 +99,6 @@ struct JssLaunch {           // per-launch arguments
     int32_t tile_begin, tile_end;
     int32_t mode;            // JSS_MODE_*
     int32_t rule, coin_mode, n_steps, write_obs;
-    int32_t range_sms, range_per_sm;   // mixed step kernel: CTA -> range permutation (0: identity)
     int32_t export_after;    // step through the generic kernel: also decode the new state into the x_* arrays (facade)
     uint64_t seed, step_index;
     double cr_factor;        // CriticalRatio due_date_factor (dispatching.py:337-349); reference default 1.5
