@@ -56,7 +56,8 @@ extern "C" {
 #define JSS_ERR_INVALID (-1)     /* bad argument */
 #define JSS_ERR_NO_DEVICE (-2)   /* no CUDA device / wrong architecture */
 #define JSS_ERR_CUDA (-3)        /* a CUDA runtime call failed (see jss_last_error) */
-#define JSS_ERR_UNSUPPORTED (-4) /* instance exceeds JSS_MAX_* or has a zero duration */
+#define JSS_ERR_UNSUPPORTED (-4) /* instance exceeds JSS_MAX_*, or has a zero-length op (the reference cannot finish such an
+                                    episode either: jss_env.py:529 never sees the op as completed) */
 #define JSS_ERR_STATE (-5)       /* call order violated (e.g. step before load/assign) */
 
 /* special actions */

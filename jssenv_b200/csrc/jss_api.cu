@@ -366,8 +366,9 @@ int jss_load_instances(jss_t *h, int n_inst, const int32_t *jobs, const int32_t 
             for (int i = 0; i < M; i++) {
                 const int m = mm[j * M + i], t = dd[j * M + i];
                 if (m < 0 || m >= M) return fail(h, JSS_ERR_INVALID, "instance %d: machine %d out of range", k, m);
-                // zero-length ops would put an event at the current time, which the
-                // queue-free time advance cannot represent
+                // Zero-length ops are rejected: the reference itself cannot finish such an episode -- an allocated op of
+                // duration 0 never satisfies `was_left_time > 0` (jss_env.py:529), so the job never advances to its
+                // next op and is re-legalised on the same machine at the same instant (jss_env.py:616-634).
                 if (t < 1 || t > JSS_MAX_DURATION)
                     return fail(h, JSS_ERR_UNSUPPORTED, "instance %d: duration %d outside [1, %d]", k, t,
                                 JSS_MAX_DURATION);
