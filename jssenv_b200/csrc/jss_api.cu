@@ -74,6 +74,8 @@ struct jss_handle {
     uint16_t *d_ops = nullptr, *d_rem = nullptr;
     int32_t *d_len = nullptr;
     unsigned long long *d_stats = nullptr;
+    uint32_t *d_tail = nullptr;                     // [2] ticket counters of the uniform step kernel's dynamic tail
+    int tail_parity = 0;
 
     JssParams p{};
     JssSmemLayout sl_env{}, sl_step{};               // shared-memory layouts of the generic / step kernels
@@ -170,6 +172,20 @@ int launch_step_uniform(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStre
     int rc = step_grid_for(h, kern, slot, smem);
     if (rc) return rc;
     const int grid = std::min(a.tile_end, h->step_grid[slot]);
+    {
+        // Static strided tiles give every CTA floor(T / grid) tiles; the remainder (T mod grid tiles) would make some CTAs
+        // run one tile longer than the rest -- those envs are drawn by ticket instead (launch k uses counter k & 1 and
+        // zeroes the other one for its successor, which cannot start drawing before this grid has completed).
+        static const bool tail_on = !(getenv("JSS_TAIL") && getenv("JSS_TAIL")[0] == '0');
+        const int rounds = a.tile_end / grid;
+        if (tail_on && rounds >= 4 && rounds * grid != a.tile_end) {
+            a.tile_end = rounds * grid;
+            a.tail_base = a.tile_end * JSS_WARPS_PER_CTA;
+            a.tail_ctr = h->d_tail + h->tail_parity;
+            a.tail_zero = h->d_tail + (h->tail_parity ^ 1);
+            h->tail_parity ^= 1;
+        }
+    }
     if (h->use_pdl) JSS_CUDA(h, JSS_LAUNCH_PDL(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl));
     else JSS_LAUNCH(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl);
     JSS_CUDA(h, cudaGetLastError());
@@ -613,6 +629,7 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
     if ((rc = dev_alloc(h, &p.last_return, (size_t)N))) return rc;
     if ((rc = dev_alloc(h, &p.acc, (size_t)N * 4))) return rc;
     if ((rc = dev_alloc(h, &h->d_stats, (size_t)JSS_STATS_LEN))) return rc;
+    if ((rc = dev_alloc(h, &h->d_tail, (size_t)4))) return rc;                 // zero-initialised
     if ((rc = dev_alloc(h, &h->dev_actions, (size_t)N))) return rc;
     h->assigned = true;
     // a fresh batch starts reset, like a freshly constructed + reset reference env

@@ -1061,13 +1061,21 @@ struct JssWarpSmem {        // per-warp shared-memory regions of the step kernel
 
 // env handled by `warp` in `tile` (-1: none) and where its state block lives (16-byte units)
 template <bool UNI>
-JSS_DEV int jss_tile_env(const JssParams &p, const SmInst *uni, int tile, int tile_end, int warp, uint32_t &off16,
-                         uint32_t &blk16) {
+JSS_DEV int jss_tile_env(const JssParams &p, const JssLaunch &a, int tile, int tile_end, int warp, int lane,
+                         uint32_t &off16, uint32_t &blk16) {
     if (UNI) {                           // env = 8 * tile + warp, block = env * block_words: nothing to load
-        const int e = tile * JSS_WARPS_PER_CTA + warp;
-        blk16 = (uint32_t)uni->block_words >> 2;
+        int e = tile * JSS_WARPS_PER_CTA + warp;
+        blk16 = (uint32_t)a.uni.block_words >> 2;
+        if (tile >= tile_end) {
+            // dynamic tail: the tiles that do not divide evenly among the persistent CTAs are handed out env by env to
+            // whichever warp gets there first, so all warps finish within one env-step of each other
+            if (a.tail_ctr == nullptr) return -1;
+            int t = 0;
+            if (lane == 0) t = (int)atomicAdd(a.tail_ctr, 1u);
+            e = a.tail_base + __shfl_sync(JSS_FULL, t, 0);
+        }
         off16 = (uint32_t)e * blk16;
-        return (tile < tile_end && e < p.n_envs) ? e : -1;
+        return e < p.n_envs ? e : -1;
     }
     if (tile >= tile_end) return -1;
     const int4 td = *reinterpret_cast<const int4 *>(p.tiles + tile);     // JssTile, one 16-byte load
@@ -1080,10 +1088,11 @@ JSS_DEV int jss_tile_env(const JssParams &p, const SmInst *uni, int tile, int ti
 // where the state block of warp `warp` of `tile` lives (16-byte units); recomputed after the step instead of
 // being carried in registers across it
 template <bool UNI>
-JSS_DEV void jss_tile_state(const JssParams &p, const SmInst *uni, int tile, int warp, uint32_t &off16, uint32_t &blk16) {
+JSS_DEV void jss_tile_state(const JssParams &p, const SmInst *uni, int tile, int warp, int env, uint32_t &off16,
+                            uint32_t &blk16) {
     if (UNI) {
         blk16 = (uint32_t)uni->block_words >> 2;
-        off16 = (uint32_t)(tile * JSS_WARPS_PER_CTA + warp) * blk16;
+        off16 = (uint32_t)env * blk16;
     } else {
         const int4 td = *reinterpret_cast<const int4 *>(p.tiles + tile);
         blk16 = (uint32_t)td.w;
@@ -1099,13 +1108,14 @@ JSS_DEV void jss_step_tiles(const JssParams &p, const JssLaunch &a, const JssSme
     int env_next, act_next = 0;
     {
         uint32_t off16, blk16;
-        env_next = jss_tile_env<UNI>(p, &a.uni, tile, tile_end, warp, off16, blk16);
+        env_next = jss_tile_env<UNI>(p, a, tile, tile_end, warp, lane, off16, blk16);
         if (env_next >= 0) {
             if (lane == 0) jss_bulk_load(w.state_sa, p.state + (size_t)off16 * 4, blk16 * 16u, w.mbar);
             act_next = a.actions[env_next];
         }
     }
-    for (; tile < tile_end; tile += tile_step) {
+    // uniform batches with a dynamic tail keep going past their static tiles for as long as tickets yield envs
+    for (; tile < tile_end || (UNI && env_next >= 0); tile += tile_step) {
         if (!UNI) {
             const int inst = p.tiles[tile].inst_count >> 8;
             if (inst != staged) {                        // CTA-uniform
@@ -1125,7 +1135,7 @@ JSS_DEV void jss_step_tiles(const JssParams &p, const JssLaunch &a, const JssSme
         }
         {   // prefetch the next env's block + action
             uint32_t off16, blk16;
-            env_next = jss_tile_env<UNI>(p, &a.uni, tile + tile_step, tile_end, warp, off16, blk16);
+            env_next = jss_tile_env<UNI>(p, a, tile + tile_step, tile_end, warp, lane, off16, blk16);
             if (env_next >= 0) {
                 if (lane == 0) jss_bulk_load(w.state_sa, p.state + (size_t)off16 * 4, blk16 * 16u, w.mbar);
                 act_next = a.actions[env_next];
@@ -1147,7 +1157,7 @@ JSS_DEV void jss_step_tiles(const JssParams &p, const JssLaunch &a, const JssSme
             // new state -> shared staging -> one bulk store (every word of the block is rewritten)
             env_store_to<KJ>(p, iv, w.state_out, lane, s);
             uint32_t off16, blk16;
-            jss_tile_state<UNI>(p, &a.uni, tile, warp, off16, blk16);
+            jss_tile_state<UNI>(p, &a.uni, tile, warp, env, off16, blk16);
             env_emit_all<KJ, true>(p, iv, s, env, lane, w.scratch, raw, w.scratch_sa,
                                    p.state + (size_t)off16 * 4, w.state_out_sa, blk16 * 16u);
         } else if (s.flags != flags_in) {                // only the sticky error bit changed
@@ -1161,10 +1171,16 @@ JSS_DEV void jss_step_tiles(const JssParams &p, const JssLaunch &a, const JssSme
 }
 
 JSS_DEV void jss_step_carve(const JssSmemLayout &sl, char *sm, int warp, JssWarpSmem &w) {
-    char *wbase = sm + sl.off_warp0 + warp * sl.warp_stride;
+    int woff = sl.off_warp0 + warp * sl.warp_stride;
+#if defined(JSS_OPAQUE_WBASE) && !defined(JSS_EMU)
+    // experiment: keep the warp's region offset in ONE register instead of letting the optimiser recompute it from
+    // threadIdx (S2R + shift + multiply-add) at every use
+    asm volatile("" : "+r"(woff));
+#endif
+    char *wbase = sm + woff;
     w.state_in = reinterpret_cast<int32_t *>(wbase + 16);
     w.scratch = reinterpret_cast<float *>(wbase + sl.off_scratch);
-    w.mbar = jss_saddr(sm) + (sl.off_warp0 + warp * sl.warp_stride);   // shared-space addresses
+    w.mbar = jss_saddr(sm) + woff;   // shared-space addresses
     w.state_sa = w.mbar + 16;
     w.scratch_sa = w.mbar + sl.off_scratch;
     // state-out staging sits right behind the observation staging (both leave by bulk store)
@@ -1192,6 +1208,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     jss_stage_instance(p, p.inst[p.uniform_inst], c, (SAMPLE == 2 && a.rule >= JSS_RULE_MWR) ? JSS_STAGE_ALL : JSS_STAGE_OPS);
     __syncthreads();
     jss_pdl_wait();
+    if (a.tail_zero && blockIdx.x == 0 && threadIdx.x == 0) *a.tail_zero = 0u;   // the NEXT launch's ticket counter
     int staged = p.uniform_inst;
     uint32_t phase = 0;
     // Static strided tiles; the env after the current one is known one iteration ahead, which is what

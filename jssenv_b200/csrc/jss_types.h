@@ -99,6 +99,10 @@ struct JssLaunch {           // per-launch arguments
     int32_t tile_begin, tile_end;
     int32_t mode;            // JSS_MODE_*
     int32_t rule, coin_mode, n_steps, write_obs;
+    // uniform step kernel, dynamic tail: envs >= tail_base are drawn by ticket from *tail_ctr; the launch zeroes
+    // *tail_zero (the counter its successor will use)
+    uint32_t *tail_ctr, *tail_zero;
+    int32_t tail_base;
     int32_t export_after;    // step through the generic kernel: also decode the new state into the x_* arrays (facade)
     uint64_t seed, step_index;
     double cr_factor;        // CriticalRatio due_date_factor (dispatching.py:337-349); reference default 1.5

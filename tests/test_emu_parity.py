@@ -154,3 +154,10 @@ def test_emu_host_pipeline_packed():
 @pytest.mark.parametrize("rule", ["RANDOM", "FIFO"])
 def test_emu_rollout_record(rule):
     pc.check_rollout_record(make_env, ["ta01", "ta01", "ta51", "ta80"], rule, n_steps=300, seed=3)
+
+
+def test_emu_uniform_dynamic_tail():
+    """Uniform batch whose tile count does not divide among the persistent CTAs (emulated grid: 2 CTAs, 9 tiles): the
+    remainder envs are drawn by ticket (dynamic tail of jss_step_kernel); launches alternate the two ticket counters."""
+    pc.check_step_sample(make_env, ["ta01"] * 70, "RANDOM", n_steps=40, seed=21)
+    pc.check_step_sample(make_env, ["ta01"] * 70, "SPT", n_steps=25, seed=22)

@@ -29,3 +29,10 @@ PY
 timeout 1200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:jss_step \
     -s 300 -c 2 -f -o gpurun_out/${T}_prof_mixed python /tmp/mixed.py > gpurun_out/${T}_ncu_mixed.log 2>&1; echo "ncu mixed rc=$?"
 ls -la gpurun_out | tail -8
+# A/B: dynamic tail off, opaque warp-base variant (ta80-shaped batch only)
+JSS_TAIL=0 PROBE_NAMES=ta71,ta80 timeout 300 python tools/probe_shapes.py > gpurun_out/${T}_probe_notail.json 2>> gpurun_out/${T}_probe.err
+JSS_B200_LIB=$PWD/jssenv_b200/variants/libjss_b200_opaque.so PROBE_NAMES=ta71,ta80 timeout 300 python tools/probe_shapes.py > gpurun_out/${T}_probe_opaque.json 2>> gpurun_out/${T}_probe.err
+python -c "
+import json
+for v in ('notail','opaque'):
+    d = json.load(open('gpurun_out/${T}_probe_%s.json' % v)); print(v, {k: round(x['us_per_launch'], 1) for k, x in d.items()})"

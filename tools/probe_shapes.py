@@ -16,7 +16,8 @@ def timed(fn, k, warm=30):
 
 out = {}
 n = int(os.environ.get("PROBE_N", 65536))
-for name in ("ta01", "ta11", "ta21", "ta31", "ta41", "ta51", "ta61", "ta71"):
+names = os.environ.get("PROBE_NAMES", "ta01,ta11,ta21,ta31,ta41,ta51,ta61,ta71").split(",")
+for name in names:
     env = JssVecEnv(n, {"instance_path": name}, auto_reset=True, seed=1)
     env.reset(); acts = env.policy("RANDOM").clone()
     for _ in range(int(0.4 * env.jobs * env.machines)):          # into the middle of the episode
@@ -29,6 +30,8 @@ for name in ("ta01", "ta11", "ta21", "ta31", "ta41", "ta51", "ta61", "ta71"):
     out[f"{name}_{J}x{M}"] = {"us_per_launch": ms * 1e3, "ns_per_env_step": ms * 1e6 / n, "B_alg": 72 * J + 8 * M + 27,
                              "GBps": (72 * J + 8 * M + 27) * n / ms / 1e6}
     env.close(); del env
+if os.environ.get("PROBE_NAMES"):
+    print(json.dumps(out, indent=1)); sys.exit(0)
 # cfg2: fused K-step rollout with observations written every step
 env = JssVecEnv(4096, {"instance_path": "ta01"}, auto_reset=True, seed=1)
 env.reset()
