@@ -699,6 +699,7 @@ int jss_step_sample(jss_t *h, const int32_t *actions_dev, int rule, int coin_mod
     a.actions = actions_dev;
     a.actions_out = next_actions_dev;
     a.rule = rule; a.coin_mode = coin_mode; a.seed = seed; a.step_index = step_index; a.cr_factor = h->cr_factor;
+    a.hash_key = jss_hash_key(seed, step_index);
     return launch_all(h, a, false, (cudaStream_t)stream);
 }
 

@@ -943,41 +943,31 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
         if (a.export_after) env_export<KJ>(p, iv, s, env, lane);   // single-env facade: one launch per transition
         return;
     }
-    // JSS_MODE_ROLLOUT: n_steps x (policy -> step) with the state held in registers
+    // JSS_MODE_ROLLOUT: n_steps x (policy -> step) with the state held in registers.
+    // Trajectory recording (a.traj_obs != NULL): step k of this env writes its observation / mask / scalar record (and
+    // the action that led to it) into slot k * n_envs + env of the caller's [n_steps][N][...] buffers -- the emit helpers
+    // index their outputs by env only, so a shifted index and other base pointers are all it takes (ONE loop body).
+    const bool record = a.traj_obs != nullptr;
+    const JssOut out = record ? JssOut{a.traj_obs, a.traj_mask, a.traj_scalars} : jss_out_default(p);
     bool dirty = false;
     int raw = 0;
-    if (a.traj_obs) {
-        // trajectory recording: step k of this env writes its observation / mask / scalar record (and the action that
-        // led to it) into slot k * n_envs + env of the caller's [n_steps][N][...] buffers -- the emit helpers index
-        // their outputs by env only, so a shifted index is all it takes
-        const JssOut traj{a.traj_obs, a.traj_mask, a.traj_scalars};
-        for (int k = 0; k < a.n_steps; k++) {
-            const uint32_t h = jss_hash3(a.seed, genv, a.step_index + (uint64_t)k);
-            const int act = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
-            int r = 0;
-            const bool changed = env_step<KJ>(p, iv, s, env, lane, act, r, hz);
-            if (changed) { raw = r; dirty = true; }
-            const int slot = k * p.n_envs + env;
-            if (a.traj_actions && lane == 0) a.traj_actions[slot] = act;
-            env_emit_obs<KJ>(p, traj, iv, s, slot, lane, scratch);
-            env_emit_mask<KJ>(p, traj, iv, s, slot, lane, (s.flags & JSS_FLAG_NOOP_LEGAL) != 0u);
-            env_emit_scalars<KJ>(traj, iv, s, slot, lane, changed ? r : 0);
-        }
-    } else {
-        for (int k = 0; k < a.n_steps; k++) {
-            const uint32_t h = jss_hash3(a.seed, genv, a.step_index + (uint64_t)k);
-            const int act = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
-            int r = 0;
-            const bool changed = env_step<KJ>(p, iv, s, env, lane, act, r, hz);
-            if (changed) {
-                raw = r; dirty = true;
-                if (a.write_obs) env_emit_all<KJ>(p, iv, s, env, lane, scratch, r);
-            }
+    for (int k = 0; k < a.n_steps; k++) {
+        const uint32_t h = jss_hash3(a.seed, genv, a.step_index + (uint64_t)k);
+        const int act = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
+        int r = 0;
+        const bool changed = env_step<KJ>(p, iv, s, env, lane, act, r, hz);
+        if (changed) { raw = r; dirty = true; }
+        if (record || (changed && a.write_obs)) {
+            const int slot = record ? k * p.n_envs + env : env;
+            if (record && a.traj_actions && lane == 0) a.traj_actions[slot] = act;
+            env_emit_obs<KJ>(p, out, iv, s, slot, lane, scratch);
+            env_emit_mask<KJ>(p, out, iv, s, slot, lane, (s.flags & JSS_FLAG_NOOP_LEGAL) != 0u);
+            env_emit_scalars<KJ>(out, iv, s, slot, lane, changed ? r : 0);
         }
     }
     if (dirty) {
         env_store<KJ>(p, iv, env, lane, s);
-        if (!a.write_obs || a.traj_obs) env_emit_all<KJ>(p, iv, s, env, lane, scratch, raw);
+        if (!a.write_obs || record) env_emit_all<KJ>(p, iv, s, env, lane, scratch, raw);
     }
 }
 
@@ -1149,7 +1139,7 @@ JSS_DEV void jss_step_tiles(const JssParams &p, const JssLaunch &a, const JssSme
         __syncwarp();
         const bool changed = env_step<KJ>(p, iv, s, env, lane, action, raw, reinterpret_cast<int *>(w.scratch));
         if (SAMPLE) {
-            const uint32_t h = jss_hash3(a.seed, p.env_id_base + (uint64_t)env, a.step_index);
+            const uint32_t h = jss_hash_env(a.hash_key, p.env_id_base + (uint64_t)env);   // == jss_hash3(seed, genv, step_index)
             const int nxt = env_select_action<KJ, SAMPLE == 1>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
             if (lane == 0) a.actions_out[env] = nxt;
         }

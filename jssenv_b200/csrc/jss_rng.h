@@ -23,6 +23,19 @@ JSS_HD static inline uint32_t jss_hash3(uint64_t seed, uint64_t env, uint64_t ct
     return h;
 }
 
+// The same hash with the launch-uniform part (seed, counter) folded once per launch on the host:
+//   jss_hash3(seed, env, ctr) == jss_hash_env(jss_hash_key(seed, ctr), env)
+JSS_HD static inline uint32_t jss_hash_key(uint64_t seed, uint64_t ctr) {
+    return jss_fold32(seed) ^ (jss_fold32(ctr) * 0xC2B2AE3Du + 0x27D4EB2Fu);
+}
+JSS_HD static inline uint32_t jss_hash_env(uint32_t key, uint64_t env) {
+    uint32_t h = key ^ (jss_fold32(env) * 0x9E3779B1u + 0x85EBCA77u);
+    h ^= h >> 16; h *= 0x85EBCA6Bu;
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+
 // index in [0, count) -- multiply-high, no modulo bias worth speaking of
 JSS_HD static inline uint32_t jss_pick(uint32_t h, uint32_t count) {
     return (uint32_t)(((uint64_t)h * (uint64_t)count) >> 32);

@@ -105,6 +105,8 @@ struct JssLaunch {           // per-launch arguments
     int32_t tail_base;
     int32_t export_after;    // step through the generic kernel: also decode the new state into the x_* arrays (facade)
     uint64_t seed, step_index;
+    uint32_t hash_key;       // jss_hash_key(seed, step_index), folded once per launch on the host (fused step + sampler)
+    uint32_t pad_key_;
     double cr_factor;        // CriticalRatio due_date_factor (dispatching.py:337-349); reference default 1.5
     const int32_t *actions;  // step
     int32_t *actions_out;    // policy
