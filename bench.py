@@ -454,7 +454,7 @@ def main():
         run_e2e(False, 4)
         # the split between "packed rows + host expansion" and "final fp32 rows by DMA" that balances this box's host
         # cores against its PCIe link: short calibration runs, then the timed run with the best share
-        calib = {f: run_e2e(True, 12, f) for f in (0.0, 0.15, 0.25, 0.35, 0.5)}
+        calib = {f: run_e2e(True, 24, f) for f in (0.0, 0.1, 0.2, 0.3, 0.4)}
         if world > 1:                                     # every rank must pick the same share
             t = torch.tensor([calib[f] for f in sorted(calib)], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MIN)

@@ -74,11 +74,9 @@ struct jss_handle {
     uint16_t *d_ops = nullptr, *d_rem = nullptr;
     int32_t *d_len = nullptr;
     unsigned long long *d_stats = nullptr;
-    uint32_t *d_tail = nullptr;                     // [2] ticket counters of the uniform step kernel's dynamic tail
-    int tail_parity = 0;
 
     JssParams p{};
-    JssSmemLayout sl_env{}, sl_step{};               // shared-memory layouts of the generic / step kernels
+    JssSmemLayout sl_env{}, sl_step{}, sl_step_rem{};   // shared-memory layouts of the generic / step kernels (step: without / with the suffix-sum table)
     int class_tile_begin[3] = {0, 0, 0}, class_tile_end[3] = {0, 0, 0};  // KJ = 1, 2, 4
     int step_grid[16] = {0};
     int env_grid[12] = {0};                         // resident CTAs per SM of the generic kernel variants (filled lazily)                        // resident-CTA grids of the step kernel variants (filled lazily)
@@ -138,9 +136,9 @@ void fill_uni(const JssInstDesc &d, SmInst &u) {
     u.f_mto = (float)d.max_time_op; u.f_mtj = (float)d.max_time_jobs; u.f_sop = (float)d.sum_op; u.f_M = (float)d.M;
     u.r_mto = d.r_mto; u.r_mtj = d.r_mtj; u.r_sop = d.r_sop; u.r_M = d.r_M;
     u.Jcap = round_up(d.J, 4); u.Mcap = round_up(d.M, 4); u.block_words = 5 * u.Jcap + u.Mcap + 12;
-    u.y14[0] = u.y14[1] = u.f_mto; u.r14[0] = u.r14[1] = d.r_mto;
-    u.y23[0] = u.f_M; u.y23[1] = u.f_mtj; u.r23[0] = d.r_M; u.r23[1] = d.r_mtj;
-    u.y56[0] = u.y56[1] = u.f_sop; u.r56[0] = u.r56[1] = d.r_sop;
+    u.n14[0] = u.n14[1] = -u.f_mto; u.r14[0] = u.r14[1] = d.r_mto;
+    u.n23[0] = -u.f_M; u.n23[1] = -u.f_mtj; u.r23[0] = d.r_M; u.r23[1] = d.r_mtj;
+    u.n56[0] = u.n56[1] = -u.f_sop; u.r56[0] = u.r56[1] = d.r_sop;
 }
 
 template <typename Kern>
@@ -164,28 +162,13 @@ int launch_step_uniform(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStre
     fill_uni(h->descs[h->p.uniform_inst], a.uni);
     a.tile_begin = 0;
     a.tile_end = (h->n_envs + JSS_WARPS_PER_CTA - 1) / JSS_WARPS_PER_CTA;
-    (void)want_rem;
-    const JssSmemLayout &sl = h->sl_step;
+    const JssSmemLayout &sl = want_rem ? h->sl_step_rem : h->sl_step;
     const size_t smem = smem_bytes(sl);
     auto kern = jss_step_kernel<KJ, SAMPLE>;
     const int slot = (KJ == 1 ? 0 : (KJ == 2 ? 1 : 2)) * 4 + SAMPLE + (want_rem ? 1 : 0);
     int rc = step_grid_for(h, kern, slot, smem);
     if (rc) return rc;
     const int grid = std::min(a.tile_end, h->step_grid[slot]);
-    {
-        // Static strided tiles give every CTA floor(T / grid) tiles; the remainder (T mod grid tiles) would make some CTAs
-        // run one tile longer than the rest -- those envs are drawn by ticket instead (launch k uses counter k & 1 and
-        // zeroes the other one for its successor, which cannot start drawing before this grid has completed).
-        static const bool tail_on = !(getenv("JSS_TAIL") && getenv("JSS_TAIL")[0] == '0');
-        const int rounds = a.tile_end / grid;
-        if (tail_on && rounds >= 4 && rounds * grid != a.tile_end) {
-            a.tile_end = rounds * grid;
-            a.tail_base = a.tile_end * JSS_WARPS_PER_CTA;
-            a.tail_ctr = h->d_tail + h->tail_parity;
-            a.tail_zero = h->d_tail + (h->tail_parity ^ 1);
-            h->tail_parity ^= 1;
-        }
-    }
     if (h->use_pdl) JSS_CUDA(h, JSS_LAUNCH_PDL(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl));
     else JSS_LAUNCH(kern, grid, JSS_WARPS_PER_CTA * 32, smem, st, h->p, a, sl);
     JSS_CUDA(h, cudaGetLastError());
@@ -197,8 +180,7 @@ int launch_step_uniform(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStre
 template <int SAMPLE>
 int launch_step_mixed(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStream_t st) {
     JssLaunch a = a_in;
-    (void)want_rem;
-    const JssSmemLayout &sl = h->sl_step;
+    const JssSmemLayout &sl = want_rem ? h->sl_step_rem : h->sl_step;
     const size_t smem = smem_bytes(sl);
     auto kern = jss_step_mixed_kernel<SAMPLE>;
     const int slot = 12 + SAMPLE + (want_rem ? 1 : 0);
@@ -556,9 +538,11 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
         h->sl_env = sl;
         h->sl_env.warp_stride = sl.scratch_words * 4;
         h->sl_env.off_scratch = 0;
-        h->sl_step = sl;
-        h->sl_step.off_scratch = 16 + p.block_words * 4;                                   // [mbarrier][state-in]
-        h->sl_step.warp_stride = h->sl_step.off_scratch + sl.scratch_words * 4 + p.block_words * 4;   // [scratch][state-out]
+        h->sl_step_rem = sl;
+        h->sl_step_rem.off_scratch = 16 + p.block_words * 4;                               // [mbarrier][state-in]
+        h->sl_step_rem.warp_stride = h->sl_step_rem.off_scratch + sl.scratch_words * 4 + p.block_words * 4;   // [scratch][state-out]
+        h->sl_step = h->sl_step_rem;                      // launches that stage no suffix sums leave their room to the L1
+        h->sl_step.off_warp0 = h->sl_step.off_rem;
     }
 
     int rc;
@@ -629,7 +613,6 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
     if ((rc = dev_alloc(h, &p.last_return, (size_t)N))) return rc;
     if ((rc = dev_alloc(h, &p.acc, (size_t)N * 4))) return rc;
     if ((rc = dev_alloc(h, &h->d_stats, (size_t)JSS_STATS_LEN))) return rc;
-    if ((rc = dev_alloc(h, &h->d_tail, (size_t)4))) return rc;                 // zero-initialised
     if ((rc = dev_alloc(h, &h->dev_actions, (size_t)N))) return rc;
     h->assigned = true;
     // a fresh batch starts reset, like a freshly constructed + reset reference env

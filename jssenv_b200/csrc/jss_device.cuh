@@ -90,21 +90,20 @@ JSS_DEV float jss_div(float x, float y, float ry) {
 // two quotients at once on the packed-fp32 pipe (sm_100 FMUL2 / FFMA2): the same three roundings per element
 // as jss_div, so the results are identical
 #ifndef JSS_EMU
-JSS_DEV float2 jss_div2(float2 x, const float (&y)[2], const float (&ry)[2]) {
-    unsigned long long xx, yy, rr, q, e, o;
+JSS_DEV float2 jss_div2(float2 x, const float (&ny)[2], const float (&ry)[2]) {   // ny = -divisor (host-negated)
+    unsigned long long xx, nn, rr, q, e, o;
     xx = *reinterpret_cast<unsigned long long *>(&x);
-    const float2 yv = make_float2(y[0], y[1]), rv = make_float2(ry[0], ry[1]);
-    yy = *reinterpret_cast<const unsigned long long *>(&yv);
+    const float2 nv = make_float2(ny[0], ny[1]), rv = make_float2(ry[0], ry[1]);
+    nn = *reinterpret_cast<const unsigned long long *>(&nv);
     rr = *reinterpret_cast<const unsigned long long *>(&rv);
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q) : "l"(xx), "l"(rr));
-    asm("{\n .reg .b64 nq;\n .reg .b32 lo, hi;\n mov.b64 {lo, hi}, %1;\n xor.b32 lo, lo, 0x80000000;\n xor.b32 hi, hi, 0x80000000;\n"
-        " mov.b64 nq, {lo, hi};\n fma.rn.f32x2 %0, nq, %2, %3;\n}" : "=l"(e) : "l"(q), "l"(yy), "l"(xx));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(e) : "l"(q), "l"(nn), "l"(xx));      // x - q * y, exact
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(o) : "l"(e), "l"(rr), "l"(q));
     return *reinterpret_cast<float2 *>(&o);
 }
 #else
-JSS_DEV float2 jss_div2(float2 x, const float (&y)[2], const float (&ry)[2]) {
-    return make_float2(jss_div(x.x, y[0], ry[0]), jss_div(x.y, y[1], ry[1]));
+JSS_DEV float2 jss_div2(float2 x, const float (&ny)[2], const float (&ry)[2]) {
+    return make_float2(jss_div(x.x, -ny[0], ry[0]), jss_div(x.y, -ny[1], ry[1]));
 }
 #endif
 
@@ -486,9 +485,9 @@ JSS_DEV void env_emit_obs(const JssParams &p, const JssOut &out, const InstView 
             const int perf = (s.todo[i] < iv.si->M) ? s.t - s.total_idle[i] : len;
             v[7 * i + 0] = (s.lb & (1u << i)) ? 1.0f : 0.0f;
             // columns that share a divisor (or sit next to each other) go through the packed-fp32 pipe in pairs
-            const float2 q14 = jss_div2(make_float2((float)s.tufco[i], (float)s.col4[i]), iv.si->y14, iv.si->r14);
-            const float2 q23 = jss_div2(make_float2((float)s.todo[i], (float)perf), iv.si->y23, iv.si->r23);
-            const float2 q56 = jss_div2(make_float2((float)s.idle_last[i], (float)s.total_idle[i]), iv.si->y56, iv.si->r56);
+            const float2 q14 = jss_div2(make_float2((float)s.tufco[i], (float)s.col4[i]), iv.si->n14, iv.si->r14);
+            const float2 q23 = jss_div2(make_float2((float)s.todo[i], (float)perf), iv.si->n23, iv.si->r23);
+            const float2 q56 = jss_div2(make_float2((float)s.idle_last[i], (float)s.total_idle[i]), iv.si->n56, iv.si->r56);
             v[7 * i + 1] = q14.x; v[7 * i + 4] = q14.y;
             v[7 * i + 2] = q23.x; v[7 * i + 3] = q23.y;
             v[7 * i + 5] = q56.x; v[7 * i + 6] = q56.y;
@@ -836,6 +835,8 @@ JSS_DEV void jss_cta_carve(const JssSmemLayout &sl, char *sm, JssCtaSmem &c, Ins
 #define JSS_STAGE_OPS 1     // ops + jobs_length
 #define JSS_STAGE_REM 2     // suffix sums (rules MWR / LWR / CR)
 #define JSS_STAGE_ALL 3
+// the rules that read the suffix sums; the host sizes the shared-memory layout with the same predicate
+JSS_DEV bool jss_rule_wants_rem(int rule) { return rule == JSS_RULE_MWR || rule == JSS_RULE_LWR || rule == JSS_RULE_CR; }
 
 JSS_DEV void jss_fill_sminst(const JssInstDesc &d, SmInst *si) {
     si->J = d.J; si->M = d.M; si->max_time_op = d.max_time_op; si->max_time_jobs = d.max_time_jobs;
@@ -844,9 +845,9 @@ JSS_DEV void jss_fill_sminst(const JssInstDesc &d, SmInst *si) {
     si->f_M = (float)d.M;
     si->r_mto = d.r_mto; si->r_mtj = d.r_mtj; si->r_sop = d.r_sop; si->r_M = d.r_M;
     si->Jcap = (d.J + 3) & ~3; si->Mcap = (d.M + 3) & ~3; si->block_words = 5 * si->Jcap + si->Mcap + 12;
-    si->y14[0] = si->y14[1] = si->f_mto; si->r14[0] = si->r14[1] = d.r_mto;
-    si->y23[0] = si->f_M; si->y23[1] = si->f_mtj; si->r23[0] = d.r_M; si->r23[1] = d.r_mtj;
-    si->y56[0] = si->y56[1] = si->f_sop; si->r56[0] = si->r56[1] = d.r_sop;
+    si->n14[0] = si->n14[1] = -si->f_mto; si->r14[0] = si->r14[1] = d.r_mto;
+    si->n23[0] = -si->f_M; si->n23[1] = -si->f_mtj; si->r23[0] = d.r_M; si->r23[1] = d.r_mtj;
+    si->n56[0] = si->n56[1] = -si->f_sop; si->r56[0] = si->r56[1] = d.r_sop;
 }
 
 JSS_DEV void jss_stage_instance(const JssParams &p, const JssInstDesc &d, const JssCtaSmem &c, int what) {
@@ -1004,9 +1005,7 @@ jss_env_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     int what = JSS_STAGE_OPS;
     if (MODE == JSS_MODE_ROLLOUT) what = JSS_STAGE_ALL;
     if (MODE == JSS_MODE_POLICY)
-        what = a.rule == JSS_RULE_RANDOM ? 0
-             : (a.rule == JSS_RULE_MWR || a.rule == JSS_RULE_LWR || a.rule == JSS_RULE_CR) ? (JSS_STAGE_OPS | JSS_STAGE_REM)
-             : JSS_STAGE_OPS;
+        what = a.rule == JSS_RULE_RANDOM ? 0 : jss_rule_wants_rem(a.rule) ? JSS_STAGE_ALL : JSS_STAGE_OPS;
     int staged = -1;
     for (int tile = a.tile_begin + (int)blockIdx.x; tile < a.tile_end; tile += (int)gridDim.x) {
         int first, inst, count;
@@ -1054,18 +1053,10 @@ template <bool UNI>
 JSS_DEV int jss_tile_env(const JssParams &p, const JssLaunch &a, int tile, int tile_end, int warp, int lane,
                          uint32_t &off16, uint32_t &blk16) {
     if (UNI) {                           // env = 8 * tile + warp, block = env * block_words: nothing to load
-        int e = tile * JSS_WARPS_PER_CTA + warp;
+        const int e = tile * JSS_WARPS_PER_CTA + warp;
         blk16 = (uint32_t)a.uni.block_words >> 2;
-        if (tile >= tile_end) {
-            // dynamic tail: the tiles that do not divide evenly among the persistent CTAs are handed out env by env to
-            // whichever warp gets there first, so all warps finish within one env-step of each other
-            if (a.tail_ctr == nullptr) return -1;
-            int t = 0;
-            if (lane == 0) t = (int)atomicAdd(a.tail_ctr, 1u);
-            e = a.tail_base + __shfl_sync(JSS_FULL, t, 0);
-        }
         off16 = (uint32_t)e * blk16;
-        return e < p.n_envs ? e : -1;
+        return (tile < tile_end && e < p.n_envs) ? e : -1;
     }
     if (tile >= tile_end) return -1;
     const int4 td = *reinterpret_cast<const int4 *>(p.tiles + tile);     // JssTile, one 16-byte load
@@ -1104,13 +1095,12 @@ JSS_DEV void jss_step_tiles(const JssParams &p, const JssLaunch &a, const JssSme
             act_next = a.actions[env_next];
         }
     }
-    // uniform batches with a dynamic tail keep going past their static tiles for as long as tickets yield envs
-    for (; tile < tile_end || (UNI && env_next >= 0); tile += tile_step) {
+    for (; tile < tile_end; tile += tile_step) {
         if (!UNI) {
             const int inst = p.tiles[tile].inst_count >> 8;
             if (inst != staged) {                        // CTA-uniform
                 __syncthreads();
-                jss_stage_instance(p, p.inst[inst], c, (SAMPLE == 2 && a.rule >= JSS_RULE_MWR) ? JSS_STAGE_ALL : JSS_STAGE_OPS);
+                jss_stage_instance(p, p.inst[inst], c, (SAMPLE == 2 && jss_rule_wants_rem(a.rule)) ? JSS_STAGE_ALL : JSS_STAGE_OPS);
                 staged = inst;
                 __syncthreads();
             }
@@ -1162,9 +1152,9 @@ JSS_DEV void jss_step_tiles(const JssParams &p, const JssLaunch &a, const JssSme
 
 JSS_DEV void jss_step_carve(const JssSmemLayout &sl, char *sm, int warp, JssWarpSmem &w) {
     int woff = sl.off_warp0 + warp * sl.warp_stride;
-#if defined(JSS_OPAQUE_WBASE) && !defined(JSS_EMU)
-    // experiment: keep the warp's region offset in ONE register instead of letting the optimiser recompute it from
-    // threadIdx (S2R + shift + multiply-add) at every use
+#if !defined(JSS_NO_OPAQUE_WBASE) && !defined(JSS_EMU)
+    // keep the warp's region offset in ONE register instead of letting the optimiser recompute it from threadIdx
+    // (S2R + shift + multiply-add) at every use: -1 % on the uniform ta80 step (94.0 -> 93.2 us)
     asm volatile("" : "+r"(woff));
 #endif
     char *wbase = sm + woff;
@@ -1195,10 +1185,9 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     if (lane == 0) jss_mbar_init(w.mbar);
     jss_pdl_launch_dependents();
     // prologue on read-only data (overlaps the tail of the previous launch under PDL)
-    jss_stage_instance(p, p.inst[p.uniform_inst], c, (SAMPLE == 2 && a.rule >= JSS_RULE_MWR) ? JSS_STAGE_ALL : JSS_STAGE_OPS);
+    jss_stage_instance(p, p.inst[p.uniform_inst], c, (SAMPLE == 2 && jss_rule_wants_rem(a.rule)) ? JSS_STAGE_ALL : JSS_STAGE_OPS);
     __syncthreads();
     jss_pdl_wait();
-    if (a.tail_zero && blockIdx.x == 0 && threadIdx.x == 0) *a.tail_zero = 0u;   // the NEXT launch's ticket counter
     int staged = p.uniform_inst;
     uint32_t phase = 0;
     // Static strided tiles; the env after the current one is known one iteration ahead, which is what

@@ -11,6 +11,7 @@
 
 #include <sched.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
 
@@ -263,6 +264,8 @@ bool have_avx512() {
 // dst and n need no alignment; cache-bypassing stores for the 64-byte-aligned body (the expanded batch is
 // far larger than the caches and is consumed by somebody else)
 __attribute__((target("avx2"))) void stream_copy(float *dst, const float *src, size_t n) {
+    static const bool nt = !(getenv("JSS_HOST_NT") && getenv("JSS_HOST_NT")[0] == '0');   // experiments: regular stores
+    if (!nt) { memcpy(dst, src, n * sizeof(float)); return; }
     size_t i = 0;
     while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 63u)) { dst[i] = src[i]; i++; }
     for (; i + 16 <= n; i += 16) {

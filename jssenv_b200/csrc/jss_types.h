@@ -90,8 +90,8 @@ struct SmInst {
     float f_mto, f_mtj, f_sop, f_M;       // the divisors as floats ...
     float r_mto, r_mtj, r_sop, r_M;       // ... and their correctly rounded reciprocals
     int Jcap, Mcap, block_words;          // state-block geometry of THIS instance: J, M rounded up to 4; 5*Jcap + Mcap + 12
-    // divisor / reciprocal PAIRS for the packed (f32x2) observation quotients: columns (1,4), (2,3), (5,6)
-    float y14[2], r14[2], y23[2], r23[2], y56[2], r56[2];
+    // NEGATED divisor / reciprocal PAIRS for the packed (f32x2) observation quotients: columns (1,4), (2,3), (5,6)
+    float n14[2], r14[2], n23[2], r23[2], n56[2], r56[2];
     int pad_[4];                          // 32 words: the tables behind it in shared memory stay 16-byte aligned
 };
 static_assert(sizeof(SmInst) % 16 == 0, "SmInst must keep the shared-memory tables 16-byte aligned");
@@ -99,10 +99,6 @@ struct JssLaunch {           // per-launch arguments
     int32_t tile_begin, tile_end;
     int32_t mode;            // JSS_MODE_*
     int32_t rule, coin_mode, n_steps, write_obs;
-    // uniform step kernel, dynamic tail: envs >= tail_base are drawn by ticket from *tail_ctr; the launch zeroes
-    // *tail_zero (the counter its successor will use)
-    uint32_t *tail_ctr, *tail_zero;
-    int32_t tail_base;
     int32_t export_after;    // step through the generic kernel: also decode the new state into the x_* arrays (facade)
     uint64_t seed, step_index;
     uint32_t hash_key;       // jss_hash_key(seed, step_index), folded once per launch on the host (fused step + sampler)

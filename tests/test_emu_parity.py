@@ -82,7 +82,7 @@ def test_emu_step_host():
     pc.check_step_host(make_env, "ta01", seed=1)
 
 
-@pytest.mark.parametrize("rule", ["RANDOM", "MWR"])
+@pytest.mark.parametrize("rule", ["RANDOM", "MWR", "LOR"])
 def test_emu_step_sample_fused(rule):
     pc.check_step_sample(make_env, ["ta01", "ta51", "ta80"], rule, n_steps=300, seed=12)
 
@@ -156,8 +156,7 @@ def test_emu_rollout_record(rule):
     pc.check_rollout_record(make_env, ["ta01", "ta01", "ta51", "ta80"], rule, n_steps=300, seed=3)
 
 
-def test_emu_uniform_dynamic_tail():
-    """Uniform batch whose tile count does not divide among the persistent CTAs (emulated grid: 2 CTAs, 9 tiles): the
-    remainder envs are drawn by ticket (dynamic tail of jss_step_kernel); launches alternate the two ticket counters."""
+def test_emu_uniform_many_tiles():
+    """Uniform batch with more tiles than (emulated) persistent CTAs, last tile partial."""
     pc.check_step_sample(make_env, ["ta01"] * 70, "RANDOM", n_steps=40, seed=21)
-    pc.check_step_sample(make_env, ["ta01"] * 70, "SPT", n_steps=25, seed=22)
+    pc.check_step_sample(make_env, ["ta01"] * 70, "LOR", n_steps=25, seed=22)

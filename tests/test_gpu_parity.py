@@ -74,7 +74,7 @@ def test_gpu_rollout_matches_steps(rule):
     pc.check_rollout_matches_steps(make_env, ["ta01", "ta01", "ta31", "ta51", "ta80", "ta80"], rule, n_steps=2600, seed=4)
 
 
-@pytest.mark.parametrize("rule", ["RANDOM", "SPT", "FIFO", "MWR", "CR"])
+@pytest.mark.parametrize("rule", ["RANDOM", "SPT", "FIFO", "MWR", "MOR", "LOR", "CR"])
 def test_gpu_step_sample_fused(rule):
     pc.check_step_sample(make_env, ["ta01", "ta31", "ta51", "ta80", "ta80"], rule, n_steps=2600, seed=12)
 

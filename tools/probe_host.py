@@ -31,6 +31,17 @@ for lvl, name in ((1, "expand_avx2_ms"), (0, "expand_scalar_ms")):
     L.jss_host_set_simd(lvl)
     out[name] = t(lambda: L.jss_host_expand_obs(h, ctypes.c_void_p(wire.data_ptr()), ctypes.c_void_p(sc.data_ptr()), ctypes.c_void_p(obs.data_ptr())), 5)
 L.jss_host_set_simd(2)
+# expansion while the copy engine streams into host memory (what happens inside an e2e step)
+big_dev = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+big_host = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+side = torch.cuda.Stream()
+def expand_under_dma():
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            big_host.copy_(big_dev, non_blocking=True)
+    L.jss_host_expand_obs(h, ctypes.c_void_p(wire.data_ptr()), ctypes.c_void_p(sc.data_ptr()), ctypes.c_void_p(obs.data_ptr()))
+out["expand_under_dma_ms"] = t(expand_under_dma, 10)
+torch.cuda.synchronize()
 dev = torch.empty(wire.shape, dtype=torch.uint8, device="cuda")
 def d2h():
     wire.copy_(dev, non_blocking=True); torch.cuda.synchronize()
