@@ -664,12 +664,19 @@ JSS_DEV int env_select_action(const InstView &iv, const EnvRegs<KJ> &s, int lane
     const uint32_t mine = (uint32_t)__popc(s.lb & LM);
     // inclusive prefix count of legal jobs over the lanes (ascending job index order)
     uint32_t incl = mine;
+    int njobs;
+    if (KJ == 1) {                                       // one job per lane: the prefix is a popcount of the ballot
+        const uint32_t b = __ballot_sync(JSS_FULL, mine != 0u);
+        incl = (uint32_t)__popc(b & ((2u << lane) - 1u));
+        njobs = __popc(b);
+    } else {
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const uint32_t o = __shfl_up_sync(JSS_FULL, incl, off);
-        if (lane >= off) incl += o;
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t o = __shfl_up_sync(JSS_FULL, incl, off);
+            if (lane >= off) incl += o;
+        }
+        njobs = (int)__shfl_sync(JSS_FULL, incl, 31);
     }
-    const int njobs = (int)__shfl_sync(JSS_FULL, incl, 31);
     const bool noop = (s.flags & JSS_FLAG_NOOP_LEGAL) != 0u;
     if (s.flags & JSS_FLAG_DONE) return 0;               // ignored by step (auto-reset or frozen)
     if (njobs == 0) return noop ? iv.si->J : JSS_ACTION_SKIP;   // "only the no-op is legal" (e.g. :96-97)
