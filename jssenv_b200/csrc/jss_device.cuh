@@ -408,10 +408,12 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
     while (lanes) {
         const int l = __ffs((int)lanes) - 1;
         lanes &= lanes - 1u;
-        uint32_t bits = __shfl_sync(JSS_FULL, s.lb, l) & jss_legal_mask<KJ>();
+        // KJ = 1: the lane's only job is the legal one (no need to fetch its bits, no inner loop)
+        uint32_t bits = (KJ == 1) ? 1u : (__shfl_sync(JSS_FULL, s.lb, l) & jss_legal_mask<KJ>());
+#pragma unroll 1
         while (bits) {                                  // warp-uniform: the legal jobs of lane l, ascending
-            const int i = __ffs((int)bits) - 1;
-            bits &= bits - 1u;
+            const int i = (KJ == 1) ? 0 : __ffs((int)bits) - 1;
+            bits = (KJ == 1) ? 0u : (bits & (bits - 1u));
             const uint32_t o = __shfl_sync(JSS_FULL, jss_sel<KJ>(s.op, i), l);
             const int m = (int)jss_op_m(o);
             const int end = s.t + jss_op_d(o);
