@@ -453,14 +453,24 @@ def main():
         run_e2e(True, 8)                                  # first touches: pinned buffers are allocated here, not in a timed run
         run_e2e(False, 4)
         # the split between "packed rows + host expansion" and "final fp32 rows by DMA" that balances this box's host
-        # cores against its PCIe link: short calibration runs, then the timed run with the best share
-        # (1.0 = everything by DMA: the least host-DRAM traffic, which wins when 8 ranks share one host's memory system)
-        calib = {f: run_e2e(True, 24, f) for f in (0.0, 0.1, 0.2, 0.3, 0.45, 0.7, 1.0)}
-        if world > 1:                                     # every rank must pick the same share
-            t = torch.tensor([calib[f] for f in sorted(calib)], dtype=torch.float64, device="cuda")
+        # cores against its PCIe link, and the worker layout (one CPU per worker vs. confined to the GPU's NUMA node:
+        # pinning wins on a quiet host, loses when a neighbour keeps one of the CPUs busy): short calibration runs,
+        # then the timed run with the best pair
+        # (share 1.0 = everything by DMA: the least host-DRAM traffic, which wins when 8 ranks share one host's memory system)
+        calib = {}
+        for pin in (1, 0):
+            os.environ["JSS_HOST_PIN"] = str(pin)
+            JssVecEnv.host_configure(0, local_rank)
+            for f in (0.0, 0.1, 0.2, 0.3, 0.45, 0.7, 1.0):
+                calib[(pin, f)] = run_e2e(True, 16, f)
+        keys = sorted(calib)
+        if world > 1:                                     # every rank must pick the same pair
+            t = torch.tensor([calib[k] for k in keys], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            calib = dict(zip(sorted(calib), t.tolist()))
-        f_best = max(calib, key=calib.get)
+            calib = dict(zip(keys, t.tolist()))
+        pin_best, f_best = max(calib, key=calib.get)
+        os.environ["JSS_HOST_PIN"] = str(pin_best)
+        bound = JssVecEnv.host_configure(0, local_rank)
         phase.clear()
         v_packed = run_e2e(True, args.e2e_steps, f_best)
         v_plain = run_e2e(False, max(10, args.e2e_steps // 4))
@@ -468,7 +478,8 @@ def main():
         e2e = {"value": v_packed, "unit": UNIT,
                "h2d_bytes_per_step": 4 * N,
                "d2h_bytes_per_step": N * ms_b + (N - n_dma) * ws_b + n_dma * J * 7 * 4 + 16 * N,
-               "dma_fraction": f_best, "dma_fraction_calibration": {str(k): v for k, v in calib.items()},
+               "dma_fraction": f_best, "workers_pinned": bool(pin_best),
+               "calibration": {f"pin={k[0]} dma={k[1]}": v for k, v in calib.items()},
                "steps": args.e2e_steps, "host_threads": threads, "numa_bound_cpus": bound,
                "fp32_dma_variant": {"value": v_plain, "d2h_bytes_per_step": N * ms_b + N * J * 7 * 4 + 16 * N},
                "host_ms_per_step": phase,

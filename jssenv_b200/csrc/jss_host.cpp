@@ -105,11 +105,12 @@ class Pool {
                 for (int c = 0; c < CPU_SETSIZE; c++)
                     if (CPU_ISSET(c, &set)) list.push_back(c);
         }
-        // One CPU per worker (JSS_HOST_PIN=1) is the fastest layout on an otherwise idle host, but on a shared box a busy
-        // CPU in the list stalls every parallel region (measured: sampler 0.15 -> 0.66 ms, whole e2e step 2.1 -> 2.8 ms),
-        // so by default the workers are only confined to the CPU list (the GPU's NUMA node) and the scheduler places them.
+        // One CPU per worker (default) is the fastest layout on a quiet host (e2e 31 M vs 25 M env-steps/s with workers only
+        // confined to the node), but on a shared box a busy CPU in the list stalls every parallel region; JSS_HOST_PIN=0
+        // confines the workers to the CPU list (the GPU's NUMA node) and lets the scheduler place them.  bench.py
+        // calibrates both layouts on the box it runs on.
         const char *pin_env = getenv("JSS_HOST_PIN");
-        const bool pin = (pin_env && pin_env[0] == '1') && !list.empty() && t <= (int)list.size();
+        const bool pin = !(pin_env && pin_env[0] == '0') && !list.empty() && t <= (int)list.size();
         int offset = 0;
         if (const char *lr = getenv("LOCAL_RANK")) offset = atoi(lr) * t;      // local ranks take disjoint slices
         for (int i = 1; i < t; i++) {
