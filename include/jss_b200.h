@@ -47,7 +47,7 @@ extern "C" {
 #define JSS_ABI_VERSION 2
 
 /* limits of the one-warp-per-env kernels */
-#define JSS_MAX_JOBS 128
+#define JSS_MAX_JOBS 256
 #define JSS_MAX_MACHINES 32
 #define JSS_MAX_DURATION 2047
 

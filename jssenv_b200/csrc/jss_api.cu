@@ -77,9 +77,9 @@ struct jss_handle {
 
     JssParams p{};
     JssSmemLayout sl_env{}, sl_step{}, sl_step_rem{};   // shared-memory layouts of the generic / step kernels (step: without / with the suffix-sum table)
-    int class_tile_begin[3] = {0, 0, 0}, class_tile_end[3] = {0, 0, 0};  // KJ = 1, 2, 4
-    int step_grid[16] = {0};
-    int env_grid[12] = {0};                         // resident CTAs per SM of the generic kernel variants (filled lazily)                        // resident-CTA grids of the step kernel variants (filled lazily)
+    int class_tile_begin[4] = {0, 0, 0, 0}, class_tile_end[4] = {0, 0, 0, 0};  // KJ = 1, 2, 4, 8
+    int step_grid[24] = {0};
+    int env_grid[16] = {0};                         // resident CTAs per SM of the generic kernel variants (filled lazily)                        // resident-CTA grids of the step kernel variants (filled lazily)
     bool use_pdl = true;
     std::vector<int32_t> env_inst;
 
@@ -126,8 +126,12 @@ int dev_alloc(jss_t *h, T **out, size_t count, bool zero = true) {
 }
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-inline int kj_of(int J) { return J <= 32 ? 1 : (J <= 64 ? 2 : 4); }
-inline int class_of(int kj) { return kj == 1 ? 0 : (kj == 2 ? 1 : 2); }
+inline int kj_of(int J) { return J <= 32 ? 1 : (J <= 64 ? 2 : (J <= 128 ? 4 : 8)); }
+inline int class_of(int kj) { return kj == 1 ? 0 : (kj == 2 ? 1 : (kj == 4 ? 2 : 3)); }
+// state-block geometry of an instance (must match jss_fill_sminst): per-lane slices are whole vectors
+inline int jcap_of(int J) { return J > 128 ? round_up(J, 8) : round_up(J, 4); }
+inline int block_words_of(int J, int M) { return 5 * jcap_of(J) + round_up(M, 4) + (J > 128 ? 16 : 8) + 4; }
+inline int hdr_word_of(int J, int M) { return 5 * jcap_of(J) + round_up(M, 4) + (J > 128 ? 16 : 8); }
 
 size_t smem_bytes(const JssSmemLayout &sl) { return (size_t)sl.off_warp0 + (size_t)JSS_WARPS_PER_CTA * sl.warp_stride; }
 
@@ -135,7 +139,7 @@ void fill_uni(const JssInstDesc &d, SmInst &u) {
     u.J = d.J; u.M = d.M; u.max_time_op = d.max_time_op; u.max_time_jobs = d.max_time_jobs; u.sum_op = d.sum_op;
     u.f_mto = (float)d.max_time_op; u.f_mtj = (float)d.max_time_jobs; u.f_sop = (float)d.sum_op; u.f_M = (float)d.M;
     u.r_mto = d.r_mto; u.r_mtj = d.r_mtj; u.r_sop = d.r_sop; u.r_M = d.r_M;
-    u.Jcap = round_up(d.J, 4); u.Mcap = round_up(d.M, 4); u.block_words = 5 * u.Jcap + u.Mcap + 12;
+    u.Jcap = jcap_of(d.J); u.Mcap = round_up(d.M, 4); u.block_words = block_words_of(d.J, d.M);
     u.n14[0] = u.n14[1] = -u.f_mto; u.r14[0] = u.r14[1] = d.r_mto;
     u.n23[0] = -u.f_M; u.n23[1] = -u.f_mtj; u.r23[0] = d.r_M; u.r23[1] = d.r_mtj;
     u.n56[0] = u.n56[1] = -u.f_sop; u.r56[0] = u.r56[1] = d.r_sop;
@@ -165,7 +169,7 @@ int launch_step_uniform(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStre
     const JssSmemLayout &sl = want_rem ? h->sl_step_rem : h->sl_step;
     const size_t smem = smem_bytes(sl);
     auto kern = jss_step_kernel<KJ, SAMPLE>;
-    const int slot = (KJ == 1 ? 0 : (KJ == 2 ? 1 : 2)) * 4 + SAMPLE + (want_rem ? 1 : 0);
+    const int slot = class_of(KJ) * 4 + SAMPLE + (want_rem ? 1 : 0);
     int rc = step_grid_for(h, kern, slot, smem);
     if (rc) return rc;
     const int grid = std::min(a.tile_end, h->step_grid[slot]);
@@ -177,13 +181,13 @@ int launch_step_uniform(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStre
 }
 
 // mixed batch: ONE launch over all lane classes, chunks handed out by ticket
-template <int SAMPLE>
+template <int SAMPLE, bool BIG>
 int launch_step_mixed(jss_t *h, const JssLaunch &a_in, bool want_rem, cudaStream_t st) {
     JssLaunch a = a_in;
     const JssSmemLayout &sl = want_rem ? h->sl_step_rem : h->sl_step;
     const size_t smem = smem_bytes(sl);
-    auto kern = jss_step_mixed_kernel<SAMPLE>;
-    const int slot = 12 + SAMPLE + (want_rem ? 1 : 0);
+    auto kern = jss_step_mixed_kernel<SAMPLE, BIG>;
+    const int slot = (BIG ? 20 : 16) + SAMPLE + (want_rem ? 1 : 0);
     int rc = step_grid_for(h, kern, slot, smem);
     if (rc) return rc;
     const int grid = h->p.n_cta_ranges;                   // one CTA per range (all resident: SMs x 3)
@@ -198,9 +202,15 @@ int launch_step(jss_t *h, const JssLaunch &a, cudaStream_t st) {
     const bool rem = a.rule == JSS_RULE_MWR || a.rule == JSS_RULE_LWR || a.rule == JSS_RULE_CR;
     const int sample = a.actions_out == nullptr ? 0 : (a.rule == JSS_RULE_RANDOM ? 1 : 2);
     if (h->p.uniform_inst < 0) {
-        if (sample == 0) return launch_step_mixed<0>(h, a, false, st);
-        if (sample == 1) return launch_step_mixed<1>(h, a, false, st);
-        return launch_step_mixed<2>(h, a, rem, st);
+        const bool big = h->class_tile_end[3] > h->class_tile_begin[3];     // instances with 129..256 jobs in the batch
+        if (big) {
+            if (sample == 0) return launch_step_mixed<0, true>(h, a, false, st);
+            if (sample == 1) return launch_step_mixed<1, true>(h, a, false, st);
+            return launch_step_mixed<2, true>(h, a, rem, st);
+        }
+        if (sample == 0) return launch_step_mixed<0, false>(h, a, false, st);
+        if (sample == 1) return launch_step_mixed<1, false>(h, a, false, st);
+        return launch_step_mixed<2, false>(h, a, rem, st);
     }
     const int kj = kj_of(h->insts[h->p.uniform_inst].J);
 #define JSS_STEP_UNI(KJ_)                                                               \
@@ -211,7 +221,8 @@ int launch_step(jss_t *h, const JssLaunch &a, cudaStream_t st) {
     } while (0)
     if (kj == 1) JSS_STEP_UNI(1);
     if (kj == 2) JSS_STEP_UNI(2);
-    JSS_STEP_UNI(4);
+    if (kj == 4) JSS_STEP_UNI(4);
+    JSS_STEP_UNI(8);
 #undef JSS_STEP_UNI
 }
 
@@ -221,7 +232,7 @@ int launch_variant(jss_t *h, const JssLaunch &a, const JssSmemLayout &sl, cudaSt
     const size_t smem = smem_bytes(sl);
     auto kern = jss_env_kernel<KJ, MODE>;
     // once per handle and kernel variant: opt-in to > 48 KB of dynamic shared memory, resident CTAs per SM
-    int &per_sm = h->env_grid[(KJ == 1 ? 0 : (KJ == 2 ? 1 : 2)) * 4 + (MODE == JSS_MODE_RESET ? 0 : MODE == JSS_MODE_ROLLOUT ? 1 : 2)];
+    int &per_sm = h->env_grid[class_of(KJ) * 4 + (MODE == JSS_MODE_RESET ? 0 : MODE == JSS_MODE_ROLLOUT ? 1 : 2)];
     if (per_sm == 0) {
         if (smem > 48 * 1024)
             JSS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -251,13 +262,14 @@ int launch_all(jss_t *h, JssLaunch a, bool want_rem, cudaStream_t st) {
     if (a.mode == JSS_MODE_STEP && !a.export_after) return launch_step(h, a, st);   // one launch, whatever the mix of lane classes
     (void)want_rem;
     const JssSmemLayout &sl = h->sl_env;
-    for (int c = 0; c < 3; c++) {
+    for (int c = 0; c < 4; c++) {
         a.tile_begin = h->class_tile_begin[c];
         a.tile_end = h->class_tile_end[c];
         int rc = JSS_OK;
         if (c == 0) rc = launch_class<1>(h, a, sl, st);
         else if (c == 1) rc = launch_class<2>(h, a, sl, st);
-        else rc = launch_class<4>(h, a, sl, st);
+        else if (c == 2) rc = launch_class<4>(h, a, sl, st);
+        else rc = launch_class<8>(h, a, sl, st);
         if (rc != JSS_OK) return rc;
     }
     return JSS_OK;
@@ -452,15 +464,15 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
     std::vector<JssTile> tiles;
     std::vector<uint32_t> state_off16((size_t)N), hdr_off16((size_t)N);
     std::vector<double> tile_cost;
-    for (int c = 0; c < 3; c++) h->class_tile_begin[c] = h->class_tile_end[c] = 0;
+    for (int c = 0; c < 4; c++) h->class_tile_begin[c] = h->class_tile_end[c] = 0;
     int pos = 0;
     int cur_class = -1;
     uint64_t off16 = 0;                                  // running state offset in 16-byte units
     while (pos < N) {
         const int k = env_to_inst[order[pos]];
         const int c = class_of(kj_of(h->insts[k].J));
-        const int Jc = round_up(h->insts[k].J, 4), Mc = round_up(h->insts[k].M, 4);
-        const uint32_t block16 = (uint32_t)(5 * Jc + Mc + 12) / 4;
+        const uint32_t block16 = (uint32_t)block_words_of(h->insts[k].J, h->insts[k].M) / 4;
+        const uint32_t hdr16 = (uint32_t)hdr_word_of(h->insts[k].J, h->insts[k].M) / 4;
         int end = pos;
         while (end < N && env_to_inst[order[end]] == k) end++;
         if (c != cur_class) {
@@ -477,7 +489,7 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
             t.block16 = block16;
             for (int w = 0; w < cnt; w++) {
                 state_off16[order[f + w]] = (uint32_t)(off16 + (uint64_t)w * block16);
-                hdr_off16[order[f + w]] = (uint32_t)(off16 + (uint64_t)w * block16) + (uint32_t)(5 * Jc + Mc + 8) / 4;
+                hdr_off16[order[f + w]] = (uint32_t)(off16 + (uint64_t)w * block16) + hdr16;
             }
             off16 += (uint64_t)cnt * block16;
             tiles.push_back(t);
@@ -496,14 +508,14 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
     {
         const int n_cta = std::max(1, std::min((int)tiles.size(), h->sm_count * JSS_MIN_CTAS));
         ranges.resize((size_t)n_cta);
-        for (int c = 0; c < 3; c++) {                     // c = 2: KJ = 4, c = 1: KJ = 2, c = 0: KJ = 1
+        for (int c = 0; c < 4; c++) {                     // c = 3: KJ = 8, c = 2: KJ = 4, c = 1: KJ = 2, c = 0: KJ = 1
             const int tb = h->class_tile_begin[c], n = h->class_tile_end[c] - tb;
-            const int shift = (c * n_cta) / 3;            // CTA that starts this class's Bresenham sequence
+            const int shift = (c * n_cta) / 4;            // CTA that starts this class's Bresenham sequence
             int given = 0;
             for (int k = 0; k < n_cta; k++) {
                 const int b = (k + shift) % n_cta;
                 const int upto = (int)(((int64_t)(k + 1) * n) / n_cta);
-                int32_t *lo = c == 2 ? &ranges[b].a4 : (c == 1 ? &ranges[b].a2 : &ranges[b].a1);
+                int32_t *lo = c == 3 ? &ranges[b].a8 : (c == 2 ? &ranges[b].a4 : (c == 1 ? &ranges[b].a2 : &ranges[b].a1));
                 lo[0] = tb + given; lo[1] = tb + upto;
                 given = upto;
             }
@@ -514,10 +526,10 @@ int jss_assign(jss_t *h, const int32_t *env_to_inst) {
     p.n_envs = N;
     p.jobs_max = jmax;
     p.machines_max = mmax;
-    p.Jcap = round_up(jmax, 4);
+    p.Jcap = jcap_of(jmax);
     p.Mcap = round_up(mmax, 4);
-    p.block_words = 5 * p.Jcap + p.Mcap + 12;            // batch maximum: sizes the shared-memory staging buffers
-    p.mask_stride = round_up(jmax + 1, 4);
+    p.block_words = block_words_of(jmax, mmax);          // batch maximum: sizes the shared-memory staging buffers
+    p.mask_stride = round_up(jmax + 1, jmax > 128 ? 8 : 4);   // the 8-jobs-per-lane class stores 8 mask bytes per lane
     p.create_flags = (int32_t)h->create_flags;
     p.env_id_base = h->env_id_base;
     {

@@ -1,6 +1,6 @@
 // jss_device.cuh -- sm_100a device code of the batched job-shop environment.
 //
-// One warp simulates one environment.  Lane l owns the KJ = 1, 2 or 4 consecutive jobs
+// One warp simulates one environment.  Lane l owns the KJ = 1, 2, 4 (or, for 129..256 jobs, 8) consecutive jobs
 // KJ*l .. KJ*l+KJ-1 (so its slice of every per-job array is ONE 4/8/16-byte vector
 // load/store and its slice of real_obs is 7 consecutive vectors), and lane m (< M <= 32)
 // owns machine m.  A lane keeps the legal / no-op-blocked bits of its own jobs in one
@@ -76,6 +76,12 @@ JSS_DEV uint32_t jss_op_m(uint32_t op) { return op >> JSS_OP_SHIFT; }
 JSS_DEV int jss_op_d(uint32_t op) { return (int)(op & JSS_OP_DMASK); }
 template <int KJ>
 JSS_DEV constexpr uint32_t jss_legal_mask() { return (1u << KJ) - 1u; }
+// `lb` layout: bit i = job slot i legal, bit BS + i = blocked by a no-op (BS = 4 for KJ <= 4, 8 for KJ = 8); a lane's
+// bits are one byte of the state block (KJ <= 4) or one 16-bit word (KJ = 8: 129..256 jobs)
+template <int KJ>
+JSS_DEV constexpr int jss_bs() { return KJ == 8 ? 8 : 4; }
+template <int KJ>
+JSS_DEV constexpr int jss_bits_words() { return KJ == 8 ? 16 : 8; }   // int32 words of the per-lane bits region
 
 // correctly rounded x / y for small non-negative integers given ry = RN(1/y): Markstein's
 // sequence q = RN(x*ry); r = x - q*y (exact, FMA); q' = RN(q + r*ry).  Checked exhaustively
@@ -168,6 +174,11 @@ JSS_DEV void jss_ld<4>(const int32_t *p, int (&o)[4]) {
     int4 v = *reinterpret_cast<const int4 *>(p);
     o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
 }
+template <>
+JSS_DEV void jss_ld<8>(const int32_t *p, int (&o)[8]) {
+    const int4 a = reinterpret_cast<const int4 *>(p)[0], b = reinterpret_cast<const int4 *>(p)[1];
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
 template <int KJ>
 JSS_DEV void jss_st(int32_t *p, const int (&o)[KJ]);
 template <>
@@ -177,6 +188,24 @@ JSS_DEV void jss_st<2>(int32_t *p, const int (&o)[2]) { *reinterpret_cast<int2 *
 template <>
 JSS_DEV void jss_st<4>(int32_t *p, const int (&o)[4]) {
     *reinterpret_cast<int4 *>(p) = make_int4(o[0], o[1], o[2], o[3]);
+}
+
+template <>
+JSS_DEV void jss_st<8>(int32_t *p, const int (&o)[8]) {
+    reinterpret_cast<int4 *>(p)[0] = make_int4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<int4 *>(p)[1] = make_int4(o[4], o[5], o[6], o[7]);
+}
+
+// a lane's legal / blocked bits inside the state block
+template <int KJ>
+JSS_DEV uint32_t jss_ld_bits(const int32_t *bits_region, int lane) {
+    if (KJ == 8) return reinterpret_cast<const uint16_t *>(bits_region)[lane];
+    return reinterpret_cast<const uint8_t *>(bits_region)[lane];
+}
+template <int KJ>
+JSS_DEV void jss_st_bits(int32_t *bits_region, int lane, uint32_t lb) {
+    if (KJ == 8) reinterpret_cast<uint16_t *>(bits_region)[lane] = (uint16_t)lb;
+    else reinterpret_cast<uint8_t *>(bits_region)[lane] = (uint8_t)lb;
 }
 
 // ---- state block <-> registers -----------------------------------------------------
@@ -216,8 +245,8 @@ JSS_DEV void env_load_from(const JssParams &p, const InstView &iv, const int32_t
     }
     const int32_t *tail = blk + 5 * Jc;
     s.tuam = (lane < iv.si->M) ? tail[lane] : 0;
-    s.lb = reinterpret_cast<const uint8_t *>(tail + Mc)[lane];
-    const int4 h4 = *reinterpret_cast<const int4 *>(tail + Mc + 8);
+    s.lb = jss_ld_bits<KJ>(tail + Mc, lane);
+    const int4 h4 = *reinterpret_cast<const int4 *>(tail + Mc + jss_bits_words<KJ>());
     s.t = h4.x; s.flags = (uint32_t)h4.y; s.ep_steps = h4.z; s.ep_return = h4.w;
     env_derive_ops<KJ>(iv, s, lane);
 }
@@ -242,8 +271,8 @@ JSS_DEV void env_load_for_policy(const JssParams &p, const InstView &iv, int env
     }
     s.tuam = 0;
     const int32_t *tail = blk + 5 * Jc;
-    s.lb = reinterpret_cast<const uint8_t *>(tail + Mc)[lane];
-    const int4 h4 = *reinterpret_cast<const int4 *>(tail + Mc + 8);
+    s.lb = jss_ld_bits<KJ>(tail + Mc, lane);
+    const int4 h4 = *reinterpret_cast<const int4 *>(tail + Mc + jss_bits_words<KJ>());
     s.t = h4.x; s.flags = (uint32_t)h4.y; s.ep_steps = h4.z; s.ep_return = h4.w;
     if (rule != JSS_RULE_RANDOM) env_derive_ops<KJ>(iv, s, lane);
     else {
@@ -265,9 +294,9 @@ JSS_DEV void env_store_to(const JssParams &p, const InstView &iv, int32_t *blk, 
     }
     int32_t *tail = blk + 5 * Jc;
     if (lane < Mc) tail[lane] = (lane < iv.si->M) ? s.tuam : 0;
-    reinterpret_cast<uint8_t *>(tail + Mc)[lane] = (uint8_t)s.lb;
+    jss_st_bits<KJ>(tail + Mc, lane, s.lb);
     if (lane == 0)
-        *reinterpret_cast<int4 *>(tail + Mc + 8) = make_int4(s.t, (int)s.flags, s.ep_steps, s.ep_return);
+        *reinterpret_cast<int4 *>(tail + Mc + jss_bits_words<KJ>()) = make_int4(s.t, (int)s.flags, s.ep_steps, s.ep_return);
 }
 
 template <int KJ>
@@ -335,7 +364,7 @@ JSS_DEV int env_advance(const InstView &iv, EnvRegs<KJ> &s, int lane) {
     const uint32_t free_m = __ballot_sync(JSS_FULL, lane < iv.si->M && s.tuam == 0);
 #pragma unroll
     for (int i = 0; i < KJ; i++)                          // legalisation (:616-634): free machine and not blocked
-        s.lb |= (jss_bit(free_m, jss_op_m(s.op[i])) & ~(s.lb >> (4 + i)) & 1u) << i;
+        s.lb |= (jss_bit(free_m, jss_op_m(s.op[i])) & ~(s.lb >> (jss_bs<KJ>() + i)) & 1u) << i;
     return hole;
 }
 
@@ -440,7 +469,7 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
         if (!(s.lb & (1u << i)) && s.todo[i] < iv.si->M) {
             int ts, tm;
             if (s.tufco[i] > 0) { ts = s.todo[i] + 1; tm = s.t + s.tufco[i]; }      // case 1 (:327-337); a running
-            else if (!(s.lb & (16u << i))) { ts = s.todo[i]; tm = s.t + tq; }       // last op walks nothing either way
+            else if (!(s.lb & ((1u << jss_bs<KJ>()) << i))) { ts = s.todo[i]; tm = s.t + tq; }       // last op walks nothing either way
             else { ts = iv.si->M; tm = 0; }                                         // case 2 (:366-377) / blocked
             const uint16_t *o_ptr = iv.ops + row + i * iv.si->M;
             while (ts < last && maxh > tm) {                                        // :340-342 / :380-382
@@ -496,9 +525,9 @@ JSS_DEV void env_emit_obs(const JssParams &p, const JssOut &out, const InstView 
         }
         // stage the lane's 7*KJ floats (one contiguous, bank-conflict-free run per lane) ...
         float *mine = scratch + 7 * KJ * lane;
-        if (KJ == 4) {
+        if (KJ == 4 || KJ == 8) {
 #pragma unroll
-            for (int q = 0; q < 7; q++)
+            for (int q = 0; q < 7 * KJ / 4; q++)
                 reinterpret_cast<float4 *>(mine)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         } else if (KJ == 2) {
 #pragma unroll
@@ -541,7 +570,15 @@ JSS_DEV void env_emit_mask(const JssParams &p, const JssOut &out, const InstView
                            bool noop) {
     uint8_t *row = out.mask + (size_t)env * p.mask_stride;
     const int j0 = KJ * lane;
-    if (j0 <= iv.si->J) {
+    if (KJ == 8) {
+        if (j0 <= iv.si->J) {                            // 8 mask bytes per lane: two 4-bit spreads (rows are 8-byte aligned)
+            uint32_t lo = ((s.lb & 15u) * 0x00204081u) & 0x01010101u, hi = (((s.lb >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+            const int d = iv.si->J - j0;                 // byte J is the no-op flag
+            if (d < 4) lo |= (noop ? 1u : 0u) << (8 * d);
+            else if (d < 8) hi |= (noop ? 1u : 0u) << (8 * (d - 4));
+            *reinterpret_cast<uint2 *>(row + j0) = make_uint2(lo, hi);
+        }
+    } else if (j0 <= iv.si->J) {
         // spread the legal bits to bytes: bit i -> byte i
         // bit i -> byte i: the products of the set bits land on distinct positions (no carries)
         uint32_t w = ((s.lb & jss_legal_mask<KJ>()) * 0x00204081u) & 0x01010101u;
@@ -609,7 +646,7 @@ JSS_DEV bool env_step(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, in
     if (wait) {
         if (!__any_sync(JSS_FULL, s.tuam > 0)) { s.flags |= JSS_FLAG_ERROR; return false; }   // IndexError at :517
         if (action == iv.si->J)                          // no-op (:419-428): legal -> blocked
-            s.lb = ((s.lb & LM) << 4) | (s.lb & (LM << 4));
+            s.lb = ((s.lb & LM) << jss_bs<KJ>()) | (s.lb & (LM << jss_bs<KJ>()));
     } else {                                             // job allocation (:441-481)
         if (action < 0 || action > iv.si->J) { s.flags |= JSS_FLAG_ERROR; return false; }
         const int la = action / KJ, ia = action % KJ;
@@ -627,7 +664,7 @@ JSS_DEV bool env_step(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, in
         for (int i = 0; i < KJ; i++)
             // every job waiting for machine m_a: no longer legal (:455-461), no longer
             // no-op-blocked (:464-467; illegal_actions[m][j] implies needed_machine[j]==m)
-            if (jss_op_m(s.op[i]) == m_a) s.lb &= ~(17u << i);
+            if (jss_op_m(s.op[i]) == m_a) s.lb &= ~((((1u << jss_bs<KJ>()) | 1u)) << i);
     }
     // ONE inlined copy of the time advance serves the three callers: the raw hook (exactly one
     // advance), the no-op (:429-430, at least one) and the job branch (:469-470, zero or more)
@@ -757,7 +794,7 @@ JSS_DEV void env_export(const JssParams &p, const InstView &iv, const EnvRegs<KJ
             p.x_idle_last[jb + j] = s.idle_last[i]; p.x_total_idle[jb + j] = s.total_idle[i];
             p.x_col4[jb + j] = s.col4[i];
             p.x_legal[jb + j] = (uint8_t)((s.lb >> i) & 1u);
-            p.x_blocked[jb + j] = (uint8_t)((s.lb >> (4 + i)) & 1u);
+            p.x_blocked[jb + j] = (uint8_t)((s.lb >> (jss_bs<KJ>() + i)) & 1u);
         }
     }
     if (lane < iv.si->M) p.x_tuam[(size_t)env * p.machines_max + lane] = s.tuam;
@@ -781,7 +818,7 @@ JSS_DEV void env_import(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, 
         s.total_idle[i] = valid ? p.x_total_idle[jb + j] : 0;
         s.col4[i] = valid ? p.x_col4[jb + j] : 0;
         if (valid && p.x_legal[jb + j] != 0) s.lb |= 1u << i;
-        if (valid && p.x_blocked[jb + j] != 0) s.lb |= 16u << i;
+        if (valid && p.x_blocked[jb + j] != 0) s.lb |= (1u << jss_bs<KJ>()) << i;
     }
     s.tuam = lane < iv.si->M ? p.x_tuam[(size_t)env * p.machines_max + lane] : 0;
     s.t = p.scalars[4 * (size_t)env + 2];
@@ -853,7 +890,9 @@ JSS_DEV void jss_fill_sminst(const JssInstDesc &d, SmInst *si) {
     si->f_mto = (float)d.max_time_op; si->f_mtj = (float)d.max_time_jobs; si->f_sop = (float)d.sum_op;
     si->f_M = (float)d.M;
     si->r_mto = d.r_mto; si->r_mtj = d.r_mtj; si->r_sop = d.r_sop; si->r_M = d.r_M;
-    si->Jcap = (d.J + 3) & ~3; si->Mcap = (d.M + 3) & ~3; si->block_words = 5 * si->Jcap + si->Mcap + 12;
+    // per-lane slices are whole vectors: J rounded up to 4 (to 8 for the 8-jobs-per-lane class, which also keeps 16 bits per lane)
+    si->Jcap = d.J > 128 ? ((d.J + 7) & ~7) : ((d.J + 3) & ~3); si->Mcap = (d.M + 3) & ~3;
+    si->block_words = 5 * si->Jcap + si->Mcap + (d.J > 128 ? 16 : 8) + 4;
     si->n14[0] = si->n14[1] = -si->f_mto; si->r14[0] = si->r14[1] = d.r_mto;
     si->n23[0] = -si->f_M; si->n23[1] = -si->f_mtj; si->r23[0] = d.r_M; si->r23[1] = d.r_mtj;
     si->n56[0] = si->n56[1] = -si->f_sop; si->r56[0] = si->r56[1] = d.r_sop;
@@ -1180,7 +1219,7 @@ JSS_DEV void jss_step_carve(const JssSmemLayout &sl, char *sm, int warp, JssWarp
 // Uniform batch (every env runs the same instance): static strided tiles, the per-instance scalars are
 // read from the kernel parameters (constant-bank operands), no CTA barrier after the first staging.
 template <int KJ, int SAMPLE>
-__global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, KJ == 1 ? JSS_MIN_CTAS_SMALL : JSS_MIN_CTAS)
+__global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, KJ == 1 ? JSS_MIN_CTAS_SMALL : (KJ == 8 ? 1 : JSS_MIN_CTAS))
 jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JSS_SMEM_DECL(jss_smem);
     char *sm = reinterpret_cast<char *>(jss_smem);
@@ -1212,8 +1251,8 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
 // allocation of its stand-alone kernel.  All CTAs start with the 100-job class and move on at about the same time:
 // the CTAs that share an SM mostly execute the same 40-60 KB loop body (the three together are 120 KB, more than
 // the instruction cache holds).  Instance tables are re-staged only when the instance changes.
-template <int SAMPLE>
-__global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, JSS_MIN_CTAS)
+template <int SAMPLE, bool BIG>   // BIG: the batch contains instances with 129..256 jobs (a fourth, 8-jobs-per-lane body)
+__global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, BIG ? 1 : JSS_MIN_CTAS)
 jss_step_mixed_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JSS_SMEM_DECL(jss_smem);
     char *sm = reinterpret_cast<char *>(jss_smem);
@@ -1226,10 +1265,11 @@ jss_step_mixed_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout 
     if (lane == 0) jss_mbar_init(w.mbar);
     jss_pdl_launch_dependents();
     const int4 r0 = reinterpret_cast<const int4 *>(p.cta_ranges + blockIdx.x)[0];   // [a4, b4) [a2, b2)
-    const int4 r1 = reinterpret_cast<const int4 *>(p.cta_ranges + blockIdx.x)[1];   // [a1, b1)
+    const int4 r1 = reinterpret_cast<const int4 *>(p.cta_ranges + blockIdx.x)[1];   // [a1, b1) [a8, b8)
     jss_pdl_wait();
     int staged = -1;
     uint32_t phase = 0;
+    if (BIG) jss_step_tiles<8, SAMPLE, false>(p, a, sl, iv, c, w, warp, lane, r1.z, r1.w, 1, staged, phase);   // 129..256 jobs
     jss_step_tiles<4, SAMPLE, false>(p, a, sl, iv, c, w, warp, lane, r0.x, r0.y, 1, staged, phase);
     jss_step_tiles<2, SAMPLE, false>(p, a, sl, iv, c, w, warp, lane, r0.z, r0.w, 1, staged, phase);
     jss_step_tiles<1, SAMPLE, false>(p, a, sl, iv, c, w, warp, lane, r1.x, r1.y, 1, staged, phase);

@@ -29,6 +29,7 @@ struct JssInstDesc {
 //   [5Jcap  , +Mcap)   time_until_available_machine
 //   then 8 words  = 32 bytes, byte l = lane l's job bits: bit i legal(job KJ*l+i),
 //                   bit 4+i blocked by a no-op (action_illegal_no_op)
+//                   (instances with 129..256 jobs, KJ = 8: 16 words, one 16-bit word per lane, blocked = bit 8+i)
 //        4 words  header: current_time_step, flags, episode_steps, episode_return_raw
 // Jcap / Mcap are those of the ENV'S OWN instance (J, M rounded up to a multiple of 4), not batch maxima.
 // Not stored because derivable: event queue, illegal_actions
@@ -50,7 +51,7 @@ struct JssTile {       // one CTA work item: up to `count` envs of ONE instance 
 
 struct JssCtaRange {   // mixed batches: the tiles of one persistent CTA -- an equal slice of EVERY lane class
     int32_t a4, b4, a2, b2;     // [a4, b4) KJ = 4 tiles, [a2, b2) KJ = 2 tiles,
-    int32_t a1, b1, pad_[2];    // [a1, b1) KJ = 1 tiles
+    int32_t a1, b1, a8, b8;     // [a1, b1) KJ = 1 tiles, [a8, b8) KJ = 8 tiles (instances with 129..256 jobs)
 };
 
 struct JssParams {

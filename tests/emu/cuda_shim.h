@@ -32,6 +32,8 @@ using std::min;
 struct int2 { int x, y; };
 struct alignas(16) int4 { int x, y, z, w; };
 struct float2 { float x, y; };
+struct alignas(8) uint2 { unsigned x, y; };
+static inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };

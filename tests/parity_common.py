@@ -546,7 +546,7 @@ def check_abi_error_codes(make_env):
     import pytest
     from jssenv_b200._native import NativeError
     bad = [
-        (synthetic_instance(129, 4, 1), "exceeds"),                      # J > JSS_MAX_JOBS
+        (synthetic_instance(257, 4, 1), "exceeds"),                      # J > JSS_MAX_JOBS
         (synthetic_instance(4, 33, 1), "exceeds"),                       # M > JSS_MAX_MACHINES
         ((np.zeros((3, 1), np.int32), np.ones((3, 1), np.int32)), "machines"),   # "We need at least 2 machines"
     ]
@@ -607,11 +607,11 @@ def check_dispatching_api(make_env):
     assert set(resb) == {"FIFO", "LOR"} and all(v["avg_makespan"] > 0 for v in resb.values())
 
 
-def check_tiny_uniform_batches(make_env, seed=50):
+def check_tiny_uniform_batches(make_env, seed=50, shapes=((2, 2), (3, 4), (4, 3), (4, 32), (1, 2), (5, 5)), max_steps=None):
     """Uniform batches of tiny instances (J <= 4, so Jcap = 4 and 7 * Jcap < 32): the per-warp scratch must
     still hold _check_no_op's 32-entry horizon table (shared-memory overflow in the rollout kernel).
     16 envs of one instance: fused rollout == policy + step kernels == oracle, transition for transition."""
-    for k, (J, M) in enumerate([(2, 2), (3, 4), (4, 3), (4, 32), (1, 2), (5, 5)]):
+    for k, (J, M) in enumerate(shapes):
         inst = synthetic_instance(J, M, seed + k, max_dur=30)
         n = 16
         cfg = {"instance_paths": [inst], "env_to_instance": [0] * n}
@@ -619,7 +619,7 @@ def check_tiny_uniform_batches(make_env, seed=50):
             a_env = make_env(n, cfg, seed=seed + k, auto_reset=True)
             b_env = make_env(n, cfg, seed=seed + k, auto_reset=True)
             a_env.reset(); b_env.reset()
-            n_steps = 6 * J * M + 7
+            n_steps = 6 * J * M + 7 if max_steps is None else min(max_steps, 6 * J * M + 7)
             a_env.rollout(rule, n_steps, write_obs=True)
             oracles = [OracleEnv(*inst) for _ in range(n)]
             done = [False] * n
@@ -700,3 +700,45 @@ def check_rollout_record(make_env, names, rule, n_steps, seed):
     for name in ("action_mask", "real_obs", "reward", "done", "current_time_step", "episode_count", "last_makespan"):
         assert np.array_equal(_np(getattr(a_env, name)), _np(getattr(b_env, name))), name
     assert a_env.stats() == b_env.stats()
+
+
+def check_big_uniform_batches(make_env, seed=60, max_steps=150):
+    """Uniform batches of instances with 129..256 jobs (8 jobs per lane, 16 bits per lane in the state block): fused
+    rollout == policy + step kernels == oracle; fused step + sampler; packed host path; single-env facade."""
+    check_tiny_uniform_batches(make_env, seed=seed, shapes=((130, 4), (256, 6)), max_steps=max_steps)
+    inst = synthetic_instance(200, 8, seed + 9, max_dur=50)
+    cfg = {"instance_paths": [inst], "env_to_instance": [0] * 9}
+    a_env = make_env(9, cfg, seed=seed, auto_reset=True)
+    b_env = make_env(9, cfg, seed=seed, auto_reset=True)
+    a_env.reset(); b_env.reset()
+    act_a = a_env.policy("MWR").clone()
+    b_env._step_index = 0
+    for k in range(max_steps):
+        act_b = b_env.policy("MWR")
+        assert np.array_equal(_np(act_a), _np(act_b)), k
+        b_env.step(act_b)
+        *_, act_a = a_env.step_sample(act_a, "MWR")
+        for name in ("action_mask", "real_obs", "reward", "done", "current_time_step"):
+            assert np.array_equal(_np(getattr(a_env, name)), _np(getattr(b_env, name))), (k, name)
+    # packed rows + host expansion == device real_obs, bit for bit
+    mask = np.ascontiguousarray(_np(a_env.action_mask))
+    a_env.host_step_begin(a_env.host_masked_random(mask, 7), packed=True)
+    a_env.host_wait_mask()
+    got = a_env.host_wait_obs()
+    assert np.array_equal(got.view(np.uint32), _np(a_env.real_obs).view(np.uint32))
+    # facade on a 200-job instance
+    env = JssEnv({"instance_path": inst})
+    o = OracleEnv(*inst)
+    obs, _ = env.reset(), o.reset()
+    rng = np.random.default_rng(seed)
+    for _ in range(max_steps):
+        legal = np.flatnonzero(o.legal_actions)
+        a = int(legal[rng.integers(len(legal))])
+        obs, r, done, _, _ = env.step(a)
+        oo, r2, d2, _, _ = o.step(a)
+        assert np.array_equal(obs["action_mask"], oo["action_mask"]) and np.abs(obs["real_obs"] - oo["real_obs"]).max() <= OBS_TOL
+        assert rew_close(r, r2) and done == d2
+        assert np.array_equal(env.todo_time_step_job, o.todo_time_step_job) and np.array_equal(env.machine_legal, o.machine_legal)
+        if done:
+            break
+    env.close()

@@ -112,7 +112,8 @@ def test_emu_gym_vector_adapter_autoreset():
 
 
 EDGE_SHAPES = [(1, 2, 9, True), (2, 2, 5, True), (33, 3, 30, True), (65, 5, 99, True), (127, 7, 50, True),
-               (128, 32, 2047, True), (32, 32, 200, True), (64, 20, 99, True), (17, 6, 40, False), (100, 20, 99, False)]
+               (128, 32, 2047, True), (32, 32, 200, True), (64, 20, 99, True), (17, 6, 40, False), (100, 20, 99, False),
+               (129, 3, 60, True), (200, 10, 99, True), (256, 32, 2047, True), (255, 5, 30, False)]   # 8 jobs per lane
 
 
 def test_emu_edge_shapes_and_limits():
@@ -160,3 +161,7 @@ def test_emu_uniform_many_tiles():
     """Uniform batch with more tiles than (emulated) persistent CTAs, last tile partial."""
     pc.check_step_sample(make_env, ["ta01"] * 70, "RANDOM", n_steps=40, seed=21)
     pc.check_step_sample(make_env, ["ta01"] * 70, "LOR", n_steps=25, seed=22)
+
+
+def test_emu_big_uniform_batches():
+    pc.check_big_uniform_batches(make_env, max_steps=60)

@@ -221,12 +221,13 @@ def test_gpu_host_pipeline():
 
 
 def test_gpu_edge_shapes_and_limits():
-    """Kernel limits and ragged shapes, full episodes: J = 1 .. 128, M = 2 .. 32, durations to 2047,
+    """Kernel limits and ragged shapes, full episodes: J = 1 .. 256, M = 2 .. 32, durations to 2047,
     partially filled lanes, non-permutation machine sequences."""
     shapes = [(1, 2, 9, True), (2, 2, 5, True), (33, 3, 30, True), (65, 5, 99, True), (127, 7, 50, True),
               (128, 32, 2047, True), (32, 32, 200, True), (64, 20, 99, True), (17, 6, 40, False), (100, 20, 99, False),
-              (128, 32, 99, False), (96, 31, 700, True)]
-    pc.check_synthetic_shapes(make_env, shapes, n_steps=9000, seed=100)
+              (128, 32, 99, False), (96, 31, 700, True),
+              (129, 3, 60, True), (200, 10, 99, True), (256, 32, 2047, True), (255, 5, 30, False)]      # 8 jobs per lane
+    pc.check_synthetic_shapes(make_env, shapes, n_steps=12000, seed=100)
 
 
 def test_gpu_abi_error_codes():
@@ -286,3 +287,7 @@ def test_gpu_host_pipeline_packed():
 @pytest.mark.parametrize("rule", ["RANDOM", "FIFO"])
 def test_gpu_rollout_record(rule):
     pc.check_rollout_record(make_env, ["ta01"] * 5 + ["ta31", "ta51", "ta80", "ta80"], rule, n_steps=2500, seed=3)
+
+
+def test_gpu_big_uniform_batches():
+    pc.check_big_uniform_batches(make_env, max_steps=1500)
