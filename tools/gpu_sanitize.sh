@@ -33,7 +33,10 @@ env.host_wait_obs()
 env.step_host(env.host_masked_random(mask, 2))
 st = env.stats(); print(st); assert st["envs_error"] == 0, st
 # uniform batch (kernel variant with the instance scalars in the kernel parameters) and tiny uniform batch
-for inst, n in (("ta80", 24), ((np.array([[0, 1], [1, 0], [0, 1]], np.int32), np.array([[3, 2], [2, 4], [1, 1]], np.int32)), 16)):
+rng = np.random.default_rng(0)
+big = (np.stack([rng.permutation(6) for _ in range(200)]).astype(np.int32), rng.integers(1, 40, size=(200, 6)).astype(np.int32))
+for inst, n in (("ta80", 24), ((np.array([[0, 1], [1, 0], [0, 1]], np.int32), np.array([[3, 2], [2, 4], [1, 1]], np.int32)), 16),
+                (big, 10)):       # 200 jobs: the 8-jobs-per-lane class
     e = JssVecEnv(n, {"instance_path": inst}, seed=3, auto_reset=True)
     e.reset(); a = e.policy("RANDOM").clone()
     for k in range(150):
