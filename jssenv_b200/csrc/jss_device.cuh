@@ -42,7 +42,14 @@ struct InstView {  // instance tables staged in shared memory
     const int32_t *len;
     const uint16_t *rem;
     const SmInst *si;
+    // Shape of the instance for branch conditions and loop bounds.  Uniform-batch kernels point `si` at the kernel
+    // parameters (constant bank: ptxas knows those are warp-uniform) and read it there; kernels that stage the instance
+    // in shared memory keep register copies that went through jss_uniform (jss_iv_shape).
+    int Ju, Mu;
+    bool staged;       // compile-time constant after inlining
 };
+JSS_DEV int jss_J(const InstView &iv) { return iv.staged ? iv.Ju : iv.si->J; }
+JSS_DEV int jss_M(const InstView &iv) { return iv.staged ? iv.Mu : iv.si->M; }
 
 template <int KJ>
 struct EnvRegs {
@@ -54,6 +61,36 @@ struct EnvRegs {
     uint32_t flags;
     int ep_steps, ep_return;
 };
+
+// ---- warp-uniformity hints -----------------------------------------------------------
+// ptxas proves a warp converged only while every branch on the way depends on values it KNOWS to be warp-uniform
+// (kernel parameters, blockIdx, results of vote / redux / a shuffle from a fixed lane).  One branch on a value it
+// cannot classify -- threadIdx.x >> 5, a word every lane loaded from the same shared-memory address -- and every
+// *_sync collective after it is compiled as "maybe diverged": UMOV + BRA.DIV + an out-of-line WARPSYNC stub per
+// collective, BSSY/BSYNC around each branch, nothing kept in uniform registers.  Passing the few truly uniform
+// inputs of an env-step through a lane-0 shuffle removes all of that (uniform ta80 step kernel: 30 BRA.DIV sites
+// -> 0, 2 496 -> 2 144 SASS instructions).
+JSS_DEV int jss_uniform(int v) {
+#ifdef JSS_NO_UNIFORM_HINTS
+    return v;
+#else
+    return __shfl_sync(JSS_FULL, v, 0);
+#endif
+}
+JSS_DEV uint32_t jss_uniform(uint32_t v) { return (uint32_t)jss_uniform((int)v); }
+JSS_DEV int jss_warp_index() { return jss_uniform((int)(threadIdx.x >> 5)); }
+// Where the flags word gets the hint.  Measured on B200 (profiles/r02_notes.md, session 8): every step / rollout kernel
+// gains 9..12 % except the uniform 4-jobs-per-lane step kernel (the ta71..80 shape), which executes 9 % fewer
+// instructions with the hint but stalls longer on the TMA command flush and the mbarrier poll and ends up 2 % slower
+// (94.5 vs 92.3 us per 65 536-env launch) -- that one instantiation keeps the conservative code.
+template <int KJ, bool UNI>
+JSS_DEV constexpr bool jss_hint_flags() {
+#ifdef JSS_EXP_HINT_ALL
+    return true;
+#else
+    return !(UNI && KJ == 4);
+#endif
+}
 
 // ---- small helpers --------------------------------------------------------------
 template <int KJ, typename T>
@@ -140,10 +177,17 @@ JSS_DEV void jss_mbar_wait(jss_saddr_t mbar, uint32_t phase) {
     } while (!ok);
 }
 JSS_DEV void jss_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-JSS_DEV void jss_bulk_store(void *gmem_dst, jss_saddr_t smem_src, uint32_t bytes) {
+JSS_DEV void jss_bulk_store(void *gmem_dst, jss_saddr_t smem_src, uint32_t bytes) {   // joins the open bulk group
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(gmem_dst), "r"(smem_src), "r"(bytes) : "memory");
+#ifdef JSS_EXP_TWO_COMMITS
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+}
+JSS_DEV void jss_bulk_commit() {
+#ifndef JSS_EXP_TWO_COMMITS
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
 }
 JSS_DEV void jss_bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 JSS_DEV void jss_bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -155,6 +199,7 @@ JSS_DEV void jss_bulk_load(jss_saddr_t smem_dst, const void *gmem_src, uint32_t 
 JSS_DEV void jss_mbar_wait(jss_saddr_t, uint32_t) { __syncwarp(); }
 JSS_DEV void jss_fence_async_smem() {}
 JSS_DEV void jss_bulk_store(void *gmem_dst, jss_saddr_t smem_src, uint32_t bytes) { memcpy(gmem_dst, smem_src, bytes); }
+JSS_DEV void jss_bulk_commit() {}
 JSS_DEV void jss_bulk_store_wait_read() {}
 JSS_DEV void jss_bulk_store_wait_all() {}
 #endif
@@ -213,9 +258,9 @@ JSS_DEV void jss_st_bits(int32_t *bits_region, int lane, uint32_t lb) {
 // last job) hold todo == M, i.e. they behave like finished jobs everywhere.
 template <int KJ>
 JSS_DEV void env_derive_ops(const InstView &iv, EnvRegs<KJ> &s, int lane) {
-    const int M = iv.si->M;
+    const int M = jss_M(iv);
     // lanes past the last job read row 0 (any in-bounds row: their todo == M selects JSS_OP_NONE anyway)
-    const int row = (KJ * lane < iv.si->J) ? KJ * lane * M : 0;
+    const int row = (KJ * lane < jss_J(iv)) ? KJ * lane * M : 0;
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
         // unconditional load of a clamped index + select: no divergent branch around the table lookup
@@ -227,13 +272,13 @@ JSS_DEV void env_derive_ops(const InstView &iv, EnvRegs<KJ> &s, int lane) {
 template <int KJ>
 JSS_DEV void env_clear_jobs(const InstView &iv, EnvRegs<KJ> &s) {
 #pragma unroll
-    for (int i = 0; i < KJ; i++) { s.todo[i] = iv.si->M; s.tufco[i] = 0; s.idle_last[i] = 0; s.total_idle[i] = 0; s.col4[i] = 0; }
+    for (int i = 0; i < KJ; i++) { s.todo[i] = jss_M(iv); s.tufco[i] = 0; s.idle_last[i] = 0; s.total_idle[i] = 0; s.col4[i] = 0; }
 }
 
 template <int KJ>
 JSS_DEV void env_load_from(const JssParams &p, const InstView &iv, const int32_t *blk, int lane, EnvRegs<KJ> &s) {
     const int Jc = iv.si->Jcap, Mc = iv.si->Mcap;   // geometry of the env's own instance
-    if (KJ * lane < iv.si->J) {
+    if (KJ * lane < jss_J(iv)) {
         const int32_t *q = blk + KJ * lane;
         jss_ld<KJ>(q, s.todo);
         jss_ld<KJ>(q + Jc, s.tufco);
@@ -244,7 +289,7 @@ JSS_DEV void env_load_from(const JssParams &p, const InstView &iv, const int32_t
         env_clear_jobs<KJ>(iv, s);
     }
     const int32_t *tail = blk + 5 * Jc;
-    s.tuam = (lane < iv.si->M) ? tail[lane] : 0;
+    s.tuam = (lane < jss_M(iv)) ? tail[lane] : 0;
     s.lb = jss_ld_bits<KJ>(tail + Mc, lane);
     const int4 h4 = *reinterpret_cast<const int4 *>(tail + Mc + jss_bits_words<KJ>());
     s.t = h4.x; s.flags = (uint32_t)h4.y; s.ep_steps = h4.z; s.ep_return = h4.w;
@@ -265,7 +310,7 @@ JSS_DEV void env_load_for_policy(const JssParams &p, const InstView &iv, int env
     const int32_t *blk = env_block(p, env);
     const int Jc = iv.si->Jcap, Mc = iv.si->Mcap;
     env_clear_jobs<KJ>(iv, s);
-    if (rule != JSS_RULE_RANDOM && KJ * lane < iv.si->J) {
+    if (rule != JSS_RULE_RANDOM && KJ * lane < jss_J(iv)) {
         jss_ld<KJ>(blk + KJ * lane, s.todo);
         if (rule == JSS_RULE_FIFO) jss_ld<KJ>(blk + 2 * Jc + KJ * lane, s.idle_last);
     }
@@ -293,7 +338,7 @@ JSS_DEV void env_store_to(const JssParams &p, const InstView &iv, int32_t *blk, 
         jss_st<KJ>(q + 4 * Jc, s.col4);
     }
     int32_t *tail = blk + 5 * Jc;
-    if (lane < Mc) tail[lane] = (lane < iv.si->M) ? s.tuam : 0;
+    if (lane < Mc) tail[lane] = (lane < jss_M(iv)) ? s.tuam : 0;
     jss_st_bits<KJ>(tail + Mc, lane, s.lb);
     if (lane == 0)
         *reinterpret_cast<int4 *>(tail + Mc + jss_bits_words<KJ>()) = make_int4(s.t, (int)s.flags, s.ep_steps, s.ep_return);
@@ -314,8 +359,8 @@ JSS_DEV void env_reset_regs(const InstView &iv, EnvRegs<KJ> &s, int lane) {
     s.lb = 0u;
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
-        const bool valid = KJ * lane + i < iv.si->J;
-        s.todo[i] = valid ? 0 : iv.si->M;
+        const bool valid = KJ * lane + i < jss_J(iv);
+        s.todo[i] = valid ? 0 : jss_M(iv);
         s.tufco[i] = 0; s.idle_last[i] = 0; s.total_idle[i] = 0; s.col4[i] = 0;
         if (valid) s.lb |= 1u << i;               // every job legal, no-op illegal (:160-161)
     }
@@ -331,10 +376,10 @@ JSS_DEV int env_advance(const InstView &iv, EnvRegs<KJ> &s, int lane) {
     const int tuam_old = s.tuam;
     const int diff = (int)__reduce_min_sync(JSS_FULL, (unsigned)(tuam_old > 0 ? tuam_old : JSS_INF));
     const int gap = diff - tuam_old;                      // > 0 only for machines idle before the event
-    const int hole = (int)__reduce_add_sync(JSS_FULL, (unsigned)((lane < iv.si->M && gap > 0) ? gap : 0));
+    const int hole = (int)__reduce_add_sync(JSS_FULL, (unsigned)((lane < jss_M(iv) && gap > 0) ? gap : 0));
     s.t += diff;
-    const int M = iv.si->M;
-    const int row = (KJ * lane < iv.si->J) ? KJ * lane * M : 0;   // lanes past the last job: any in-bounds row
+    const int M = jss_M(iv);
+    const int row = (KJ * lane < jss_J(iv)) ? KJ * lane * M : 0;   // lanes past the last job: any in-bounds row
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
         // branch-free form of the reference's three cases (select instructions instead of divergent
@@ -361,7 +406,7 @@ JSS_DEV int env_advance(const InstView &iv, EnvRegs<KJ> &s, int lane) {
         s.col4[i] = finished ? c4 : s.col4[i];
     }
     s.tuam = gap < 0 ? -gap : 0;
-    const uint32_t free_m = __ballot_sync(JSS_FULL, lane < iv.si->M && s.tuam == 0);
+    const uint32_t free_m = __ballot_sync(JSS_FULL, lane < jss_M(iv) && s.tuam == 0);
 #pragma unroll
     for (int i = 0; i < KJ; i++)                          // legalisation (:616-634): free machine and not blocked
         s.lb |= (jss_bit(free_m, jss_op_m(s.op[i])) & ~(s.lb >> (jss_bs<KJ>() + i)) & 1u) << i;
@@ -381,7 +426,7 @@ JSS_DEV uint32_t env_machine_legal(const EnvRegs<KJ> &s) {
 template <int KJ>
 JSS_DEV void env_prioritize(const InstView &iv, EnvRegs<KJ> &s, int lane) {
     uint32_t fin = 0u;                                    // my legal FINAL ops
-    const int last = iv.si->M - 1;
+    const int last = jss_M(iv) - 1;
 #pragma unroll
     for (int i = 0; i < KJ; i++) fin |= (s.todo[i] == last ? 1u : 0u) << i;
     fin &= s.lb;
@@ -391,14 +436,14 @@ JSS_DEV void env_prioritize(const InstView &iv, EnvRegs<KJ> &s, int lane) {
     for (int i = 0; i < KJ; i++)
         if (fin & (1u << i)) fin_m |= 1u << (jss_op_m(s.op[i]) & 31u);
     fin_m = __reduce_or_sync(JSS_FULL, fin_m);
-    const uint32_t free_m = __ballot_sync(JSS_FULL, lane < iv.si->M && s.tuam == 0);
+    const uint32_t free_m = __ballot_sync(JSS_FULL, lane < jss_M(iv) && s.tuam == 0);
     int cand_d[KJ];                                       // duration if legal non-final op whose NEXT machine is free
-    const int row = KJ * lane * iv.si->M;
+    const int row = KJ * lane * jss_M(iv);
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
         cand_d[i] = JSS_INF;
         if ((s.lb & (1u << i)) && !(fin & (1u << i))) {
-            const uint32_t nxt = iv.ops[row + i * iv.si->M + s.todo[i] + 1];
+            const uint32_t nxt = iv.ops[row + i * jss_M(iv) + s.todo[i] + 1];
             if (jss_bit(free_m, jss_op_m(nxt))) cand_d[i] = jss_op_d(s.op[i]);   // :234-239
         }
     }
@@ -454,24 +499,24 @@ JSS_DEV bool env_check_no_op(const InstView &iv, const EnvRegs<KJ> &s, int lane,
             maxh = max(maxh, cur);                      // :321
         }
     }
-    const int last = iv.si->M - 1;
+    const int last = jss_M(iv) - 1;
     // per-machine horizon table: finite only for machines that have a legal job, so the
     // walk's test `max_horizon_machine[m] > time and machine_legal[m]` is one compare
     hz[lane] = (lane == lm0) ? h0 : (lane == lm1) ? h1 : (lane == lm2) ? h2 : (int)0x80000000;
     __syncwarp();
     // pass 2 (:324-401): jobs that are not legal now but may need a legal machine soon
     uint32_t want = 0u;
-    const int row = KJ * lane * iv.si->M;
+    const int row = KJ * lane * jss_M(iv);
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
         // countdown of the job's current machine (case 2, :374-377)
         const int tq = __shfl_sync(JSS_FULL, s.tuam, (int)(jss_op_m(s.op[i]) & 31u));
-        if (!(s.lb & (1u << i)) && s.todo[i] < iv.si->M) {
+        if (!(s.lb & (1u << i)) && s.todo[i] < jss_M(iv)) {
             int ts, tm;
             if (s.tufco[i] > 0) { ts = s.todo[i] + 1; tm = s.t + s.tufco[i]; }      // case 1 (:327-337); a running
             else if (!(s.lb & ((1u << jss_bs<KJ>()) << i))) { ts = s.todo[i]; tm = s.t + tq; }       // last op walks nothing either way
-            else { ts = iv.si->M; tm = 0; }                                         // case 2 (:366-377) / blocked
-            const uint16_t *o_ptr = iv.ops + row + i * iv.si->M;
+            else { ts = jss_M(iv); tm = 0; }                                         // case 2 (:366-377) / blocked
+            const uint16_t *o_ptr = iv.ops + row + i * jss_M(iv);
             while (ts < last && maxh > tm) {                                        // :340-342 / :380-382
                 const uint32_t o = o_ptr[ts];
                 if (hz[jss_op_m(o)] > tm) want |= 1u << jss_op_m(o);                // machine_next.add (:351 / :391)
@@ -505,7 +550,7 @@ template <int KJ, bool BULK = false>
 JSS_DEV void env_emit_obs(const JssParams &p, const JssOut &out, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane,
                           float *scratch, jss_saddr_t scratch_sa = jss_saddr_t(), void *st_dst = nullptr,
                           jss_saddr_t st_sa = jss_saddr_t(), uint32_t st_bytes = 0u) {
-    if (KJ * lane < iv.si->J) {
+    if (KJ * lane < jss_J(iv)) {
         float v[KJ * 7];
 #pragma unroll
         for (int i = 0; i < KJ; i++) {
@@ -513,7 +558,7 @@ JSS_DEV void env_emit_obs(const JssParams &p, const JssOut &out, const InstView 
             // jobs_length[j] afterwards (every advance adds `difference` to exactly one of
             // the two counters until the job completes)
             const int len = iv.len[KJ * lane + i];        // unconditional (in-bounds) load + select
-            const int perf = (s.todo[i] < iv.si->M) ? s.t - s.total_idle[i] : len;
+            const int perf = (s.todo[i] < jss_M(iv)) ? s.t - s.total_idle[i] : len;
             v[7 * i + 0] = (s.lb & (1u << i)) ? 1.0f : 0.0f;
             // columns that share a divisor (or sit next to each other) go through the packed-fp32 pipe in pairs
             const float2 q14 = jss_div2(make_float2((float)s.tufco[i], (float)s.col4[i]), iv.si->n14, iv.si->r14);
@@ -538,7 +583,7 @@ JSS_DEV void env_emit_obs(const JssParams &p, const JssOut &out, const InstView 
         }
     }
     float *dst = out.obs + (size_t)env * p.jobs_max * 7;
-    const int n = iv.si->J * 7;
+    const int n = jss_J(iv) * 7;
     if (BULK) {
         // ONE proxy fence covers both staged buffers (new state block + observation rows), then lane 0
         // hands them to the TMA engine: one bulk copy shared -> global each
@@ -547,6 +592,7 @@ JSS_DEV void env_emit_obs(const JssParams &p, const JssOut &out, const InstView 
         if (lane == 0) {
             if (st_bytes) jss_bulk_store(st_dst, st_sa, st_bytes);
             if ((n & 3) == 0 && (p.jobs_max & 3) == 0) jss_bulk_store(dst, scratch_sa, (uint32_t)n * 4u);
+            jss_bulk_commit();           // ONE group for both copies (an empty group is legal)
         }
         if ((n & 3) == 0 && (p.jobs_max & 3) == 0)
             return;                      // the caller waits (wait_group.read) before reusing the staging buffers
@@ -571,23 +617,23 @@ JSS_DEV void env_emit_mask(const JssParams &p, const JssOut &out, const InstView
     uint8_t *row = out.mask + (size_t)env * p.mask_stride;
     const int j0 = KJ * lane;
     if (KJ == 8) {
-        if (j0 <= iv.si->J) {                            // 8 mask bytes per lane: two 4-bit spreads (rows are 8-byte aligned)
+        if (j0 <= jss_J(iv)) {                            // 8 mask bytes per lane: two 4-bit spreads (rows are 8-byte aligned)
             uint32_t lo = ((s.lb & 15u) * 0x00204081u) & 0x01010101u, hi = (((s.lb >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-            const int d = iv.si->J - j0;                 // byte J is the no-op flag
+            const int d = jss_J(iv) - j0;                 // byte J is the no-op flag
             if (d < 4) lo |= (noop ? 1u : 0u) << (8 * d);
             else if (d < 8) hi |= (noop ? 1u : 0u) << (8 * (d - 4));
             *reinterpret_cast<uint2 *>(row + j0) = make_uint2(lo, hi);
         }
-    } else if (j0 <= iv.si->J) {
+    } else if (j0 <= jss_J(iv)) {
         // spread the legal bits to bytes: bit i -> byte i
         // bit i -> byte i: the products of the set bits land on distinct positions (no carries)
         uint32_t w = ((s.lb & jss_legal_mask<KJ>()) * 0x00204081u) & 0x01010101u;
-        if (iv.si->J - j0 < KJ) w |= (noop ? 1u : 0u) << (8 * (iv.si->J - j0));     // byte J is the no-op flag
+        if (jss_J(iv) - j0 < KJ) w |= (noop ? 1u : 0u) << (8 * (jss_J(iv) - j0));     // byte J is the no-op flag
         if (KJ == 4) *reinterpret_cast<uint32_t *>(row + j0) = w;
         else if (KJ == 2) *reinterpret_cast<uint16_t *>(row + j0) = (uint16_t)w;
         else row[j0] = (uint8_t)w;
     }
-    if (iv.si->J == 32 * KJ && lane == 0) row[iv.si->J] = noop ? 1 : 0;   // no lane owns byte J
+    if (jss_J(iv) == 32 * KJ && lane == 0) row[jss_J(iv)] = noop ? 1 : 0;   // no lane owns byte J
 }
 
 // reward / raw reward / time / (flags << 8 | done) of an env are ONE 16-byte record, so the
@@ -642,13 +688,13 @@ JSS_DEV bool env_step(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, in
     }
     constexpr uint32_t LM = jss_legal_mask<KJ>();
     int holes = 0, gain = 0;
-    const bool wait = (action == JSS_ACTION_ADVANCE || action == iv.si->J);
+    const bool wait = (action == JSS_ACTION_ADVANCE || action == jss_J(iv));
     if (wait) {
         if (!__any_sync(JSS_FULL, s.tuam > 0)) { s.flags |= JSS_FLAG_ERROR; return false; }   // IndexError at :517
-        if (action == iv.si->J)                          // no-op (:419-428): legal -> blocked
+        if (action == jss_J(iv))                          // no-op (:419-428): legal -> blocked
             s.lb = ((s.lb & LM) << jss_bs<KJ>()) | (s.lb & (LM << jss_bs<KJ>()));
     } else {                                             // job allocation (:441-481)
-        if (action < 0 || action > iv.si->J) { s.flags |= JSS_FLAG_ERROR; return false; }
+        if (action < 0 || action > jss_J(iv)) { s.flags |= JSS_FLAG_ERROR; return false; }
         const int la = action / KJ, ia = action % KJ;
         const uint32_t opa = __shfl_sync(JSS_FULL, jss_sel<KJ>(s.op, ia), la);
         const uint32_t bits_a = __shfl_sync(JSS_FULL, s.lb, la);
@@ -677,7 +723,7 @@ JSS_DEV bool env_step(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, in
         force = false;
         if (action == JSS_ACTION_ADVANCE) { raw_reward = -holes; return true; }   // heuristics / _is_done do NOT run
     }
-    if (action == iv.si->J && !(st & 1u))
+    if (action == jss_J(iv) && !(st & 1u))
         s.flags |= JSS_FLAG_ERROR;                       // the reference raises here (queue ran empty)
     raw_reward = gain - holes;
     env_prioritize<KJ>(iv, s, lane);                     // :432 / :471
@@ -718,11 +764,11 @@ JSS_DEV int env_select_action(const InstView &iv, const EnvRegs<KJ> &s, int lane
     }
     const bool noop = (s.flags & JSS_FLAG_NOOP_LEGAL) != 0u;
     if (s.flags & JSS_FLAG_DONE) return 0;               // ignored by step (auto-reset or frozen)
-    if (njobs == 0) return noop ? iv.si->J : JSS_ACTION_SKIP;   // "only the no-op is legal" (e.g. :96-97)
+    if (njobs == 0) return noop ? jss_J(iv) : JSS_ACTION_SKIP;   // "only the no-op is legal" (e.g. :96-97)
     if (RANDOM_ONLY || rule == JSS_RULE_RANDOM) {
         // uniform over the set bits of action_mask, indexed in ascending action order
         const uint32_t r = jss_pick(h, (uint32_t)(njobs + (noop ? 1 : 0)));
-        if ((int)r == njobs) return iv.si->J;
+        if ((int)r == njobs) return jss_J(iv);
         const uint32_t before = incl - mine;
         const bool own = r >= before && r < incl;
         int act = 0;
@@ -745,7 +791,7 @@ JSS_DEV int env_select_action(const InstView &iv, const EnvRegs<KJ> &s, int lane
             const int j = KJ * lane + i;
             if (s.lb & (1u << i)) {
                 const double due = (double)iv.len[j] * cr_factor;                    // :357-360
-                const int remaining = iv.rem[j * (iv.si->M + 1) + s.todo[i]];            // :387-388
+                const int remaining = iv.rem[j * (jss_M(iv) + 1) + s.todo[i]];            // :387-388
                 const double ratio = remaining > 0 ? (due - (double)s.t) / (double)remaining : 1.0 / 0.0;
                 if (ratio < key) { key = ratio; kj = j; }                            // strict <, first index wins
             }
@@ -769,8 +815,8 @@ JSS_DEV int env_select_action(const InstView &iv, const EnvRegs<KJ> &s, int lane
                 if (rule == JSS_RULE_SPT) key = (uint32_t)jss_op_d(s.op[i]);                    // :105-108
                 else if (rule == JSS_RULE_FIFO) key = (uint32_t)s.idle_last[i];                 // :146-148
                 else if (rule == JSS_RULE_MWR || rule == JSS_RULE_LWR)
-                    key = iv.rem[j * (iv.si->M + 1) + s.todo[i]];                                   // :188-191 / :231-234
-                else key = (uint32_t)(iv.si->M - s.todo[i]);                                        // :273 / :314
+                    key = iv.rem[j * (jss_M(iv) + 1) + s.todo[i]];                                   // :188-191 / :231-234
+                else key = (uint32_t)(jss_M(iv) - s.todo[i]);                                        // :273 / :314
                 const uint32_t c = minimise ? ((key << 8) | (uint32_t)j) : ((key << 8) | (uint32_t)(255 - j));
                 comp = minimise ? min(comp, c) : max(comp, c);
             }
@@ -778,7 +824,7 @@ JSS_DEV int env_select_action(const InstView &iv, const EnvRegs<KJ> &s, int lane
         comp = minimise ? __reduce_min_sync(JSS_FULL, comp) : __reduce_max_sync(JSS_FULL, comp);
         best = minimise ? (int)(comp & 255u) : 255 - (int)(comp & 255u);
     }
-    if (noop && coin_mode == JSS_COIN_DEVICE && h < JSS_COIN_THRESHOLD) return iv.si->J;   // e.g. :113-114
+    if (noop && coin_mode == JSS_COIN_DEVICE && h < JSS_COIN_THRESHOLD) return jss_J(iv);   // e.g. :113-114
     return best;
 }
 
@@ -789,7 +835,7 @@ JSS_DEV void env_export(const JssParams &p, const InstView &iv, const EnvRegs<KJ
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
         const int j = KJ * lane + i;
-        if (j < iv.si->J) {
+        if (j < jss_J(iv)) {
             p.x_todo[jb + j] = s.todo[i]; p.x_tufco[jb + j] = s.tufco[i];
             p.x_idle_last[jb + j] = s.idle_last[i]; p.x_total_idle[jb + j] = s.total_idle[i];
             p.x_col4[jb + j] = s.col4[i];
@@ -797,7 +843,7 @@ JSS_DEV void env_export(const JssParams &p, const InstView &iv, const EnvRegs<KJ
             p.x_blocked[jb + j] = (uint8_t)((s.lb >> (jss_bs<KJ>() + i)) & 1u);
         }
     }
-    if (lane < iv.si->M) p.x_tuam[(size_t)env * p.machines_max + lane] = s.tuam;
+    if (lane < jss_M(iv)) p.x_tuam[(size_t)env * p.machines_max + lane] = s.tuam;
     if (lane == 0) {
         p.scalars[4 * (size_t)env + 2] = s.t;
         p.scalars[4 * (size_t)env + 3] = (int32_t)((s.flags << 8) | (s.flags & JSS_FLAG_DONE));
@@ -811,8 +857,8 @@ JSS_DEV void env_import(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, 
 #pragma unroll
     for (int i = 0; i < KJ; i++) {
         const int j = KJ * lane + i;
-        const bool valid = j < iv.si->J;
-        s.todo[i] = valid ? p.x_todo[jb + j] : iv.si->M;
+        const bool valid = j < jss_J(iv);
+        s.todo[i] = valid ? p.x_todo[jb + j] : jss_M(iv);
         s.tufco[i] = valid ? p.x_tufco[jb + j] : 0;
         s.idle_last[i] = valid ? p.x_idle_last[jb + j] : 0;
         s.total_idle[i] = valid ? p.x_total_idle[jb + j] : 0;
@@ -820,7 +866,7 @@ JSS_DEV void env_import(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, 
         if (valid && p.x_legal[jb + j] != 0) s.lb |= 1u << i;
         if (valid && p.x_blocked[jb + j] != 0) s.lb |= (1u << jss_bs<KJ>()) << i;
     }
-    s.tuam = lane < iv.si->M ? p.x_tuam[(size_t)env * p.machines_max + lane] : 0;
+    s.tuam = lane < jss_M(iv) ? p.x_tuam[(size_t)env * p.machines_max + lane] : 0;
     s.t = p.scalars[4 * (size_t)env + 2];
     s.flags = (uint32_t)p.scalars[4 * (size_t)env + 3] >> 8;
     env_derive_ops<KJ>(iv, s, lane);
@@ -833,7 +879,7 @@ JSS_DEV void env_import(const JssParams &p, const InstView &iv, EnvRegs<KJ> &s, 
 template <int KJ>
 JSS_DEV void env_pack(const JssLaunch &a, const InstView &iv, const EnvRegs<KJ> &s, int env, int lane, float *scratch) {
     uint16_t *st = reinterpret_cast<uint16_t *>(scratch);
-    if (KJ * lane < iv.si->J) {
+    if (KJ * lane < jss_J(iv)) {
 #pragma unroll
         for (int i = 0; i < KJ; i++) {
             const uint32_t w0 = ((s.lb >> i) & 1u) | ((uint32_t)s.tufco[i] << 1) | ((uint32_t)s.todo[i] << 12) |
@@ -848,7 +894,7 @@ JSS_DEV void env_pack(const JssLaunch &a, const InstView &iv, const EnvRegs<KJ> 
     }
     __syncwarp();
     uint4 *dst = reinterpret_cast<uint4 *>(a.wire + (size_t)env * a.wire_stride);
-    const int n16 = (iv.si->J * 10 + 15) >> 4;
+    const int n16 = (jss_J(iv) * 10 + 15) >> 4;
     for (int k = lane; k < n16; k += 32) dst[k] = reinterpret_cast<const uint4 *>(scratch)[k];
     __syncwarp();
 }
@@ -875,7 +921,13 @@ JSS_DEV void jss_cta_carve(const JssSmemLayout &sl, char *sm, JssCtaSmem &c, Ins
     c.ops = reinterpret_cast<uint16_t *>(sm + sizeof(SmInst));
     c.len = reinterpret_cast<int32_t *>(sm + sl.off_len);
     c.rem = reinterpret_cast<uint16_t *>(sm + sl.off_rem);
-    iv.ops = c.ops; iv.len = c.len; iv.rem = c.rem; iv.si = c.si;
+    iv.ops = c.ops; iv.len = c.len; iv.rem = c.rem; iv.si = c.si; iv.staged = true; iv.Ju = iv.Mu = 0;
+}
+
+// refresh the uniform register copies of J / M from the staged instance (one packed shuffle)
+JSS_DEV void jss_iv_shape(InstView &iv) {
+    const uint32_t jm = jss_uniform((uint32_t)iv.si->J | ((uint32_t)iv.si->M << 16));
+    iv.Ju = (int)(jm & 0xffffu); iv.Mu = (int)(jm >> 16);
 }
 
 #define JSS_STAGE_OPS 1     // ops + jobs_length
@@ -966,6 +1018,7 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
     const uint64_t genv = p.env_id_base + (uint64_t)env;
     if (mode == JSS_MODE_POLICY) env_load_for_policy<KJ>(p, iv, env, lane, s, a.rule);
     else env_load<KJ>(p, iv, env, lane, s);
+    s.flags = jss_uniform(s.flags);                      // one word read by every lane (see jss_uniform)
     if (mode == JSS_MODE_EXPORT) { env_export<KJ>(p, iv, s, env, lane); return; }
     if (mode == JSS_MODE_PACK) { env_pack<KJ>(a, iv, s, env, lane, scratch); return; }
     if (mode == JSS_MODE_POLICY) {
@@ -975,10 +1028,11 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
         return;
     }
     if (mode == JSS_MODE_STEP) {
-        const int action = a.actions[env];
+        const int action = jss_uniform(a.actions[env]);
         int raw = 0;
         const uint32_t flags_in = s.flags;
         const bool changed = env_step<KJ>(p, iv, s, env, lane, action, raw, hz);
+        s.flags = jss_uniform(s.flags);
         if (changed) {
             env_store<KJ>(p, iv, env, lane, s);
             env_emit_all<KJ>(p, iv, s, env, lane, scratch, raw);
@@ -1002,9 +1056,10 @@ JSS_DEV void jss_process_env(const JssParams &p, const JssLaunch &a, const InstV
     int raw = 0;
     for (int k = 0; k < a.n_steps; k++) {
         const uint32_t h = jss_hash3(a.seed, genv, a.step_index + (uint64_t)k);
-        const int act = env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
+        const int act = jss_uniform(env_select_action<KJ>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor));
         int r = 0;
         const bool changed = env_step<KJ>(p, iv, s, env, lane, act, r, hz);
+        s.flags = jss_uniform(s.flags);
         if (changed) { raw = r; dirty = true; }
         if (record || (changed && a.write_obs)) {
             const int slot = record ? k * p.n_envs + env : env;
@@ -1046,7 +1101,7 @@ jss_env_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JssCtaSmem c;
     InstView iv;
     jss_cta_carve(sl, sm, c, iv);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = jss_warp_index(), lane = threadIdx.x & 31;
     float *scratch = reinterpret_cast<float *>(sm + sl.off_warp0 + warp * sl.warp_stride);
     // what the mode reads: the masked-uniform sampler looks at no instance table at all (only J); the other policies
     // at ops / len (+ suffix sums for MWR / LWR / CR); everything that steps needs all tables
@@ -1058,15 +1113,17 @@ jss_env_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     for (int tile = a.tile_begin + (int)blockIdx.x; tile < a.tile_end; tile += (int)gridDim.x) {
         int first, inst, count;
         jss_tile_desc(p, tile, first, inst, count);
+        first = jss_uniform(first); inst = jss_uniform(inst); count = jss_uniform(count);
         if (inst != staged) {                            // CTA-uniform
             __syncthreads();
             jss_stage_instance(p, p.inst[inst], c, what);
             staged = inst;
             __syncthreads();
         }
+        jss_iv_shape(iv);
         if (warp < count)
-            jss_process_env<KJ, MODE>(p, a, iv, p.uniform_inst >= 0 ? first + warp : p.order[first + warp], lane,
-                                      scratch);
+            jss_process_env<KJ, MODE>(p, a, iv, p.uniform_inst >= 0 ? first + warp : jss_uniform(p.order[first + warp]),
+                                      lane, scratch);
     }
 }
 
@@ -1152,8 +1209,9 @@ JSS_DEV void jss_step_tiles(const JssParams &p, const JssLaunch &a, const JssSme
                 staged = inst;
                 __syncthreads();
             }
+            jss_iv_shape(iv);
         }
-        const int env = env_next, action = act_next;
+        const int env = UNI ? env_next : jss_uniform(env_next), action = act_next;
         EnvRegs<KJ> s;
         if (env >= 0) {
             jss_mbar_wait(w.mbar, phase);                // this env's block has landed in shared memory
@@ -1171,11 +1229,15 @@ JSS_DEV void jss_step_tiles(const JssParams &p, const JssLaunch &a, const JssSme
         }
         if (env < 0) continue;
         int raw = 0;
-        const uint32_t flags_in = s.flags;
         // the previous env's observation must have left the staging buffer (also aliased by hz)
         if (lane == 0) jss_bulk_store_wait_read();
         __syncwarp();
+        // every lane holds the same flags word (one address, loaded by all lanes): say so -- ptxas already sees that
+        // for the action and the time, a shuffle of those is folded away
+        if (jss_hint_flags<KJ, UNI>()) s.flags = jss_uniform(s.flags);
+        const uint32_t flags_in = s.flags;
         const bool changed = env_step<KJ>(p, iv, s, env, lane, action, raw, reinterpret_cast<int *>(w.scratch));
+        if (jss_hint_flags<KJ, UNI>()) s.flags = jss_uniform(s.flags);   // the no-op test returns from inside lane-dependent code
         if (SAMPLE) {
             const uint32_t h = jss_hash_env(a.hash_key, p.env_id_base + (uint64_t)env);   // == jss_hash3(seed, genv, step_index)
             const int nxt = env_select_action<KJ, SAMPLE == 1>(iv, s, lane, a.rule, a.coin_mode, h, a.cr_factor);
@@ -1226,8 +1288,8 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
     JssCtaSmem c;
     InstView iv;
     jss_cta_carve(sl, sm, c, iv);
-    iv.si = &a.uni;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    iv.si = &a.uni; iv.staged = false;
+    const int warp = jss_warp_index(), lane = threadIdx.x & 31;
     JssWarpSmem w;
     jss_step_carve(sl, sm, warp, w);
     if (lane == 0) jss_mbar_init(w.mbar);
@@ -1259,7 +1321,7 @@ jss_step_mixed_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout 
     JssCtaSmem c;
     InstView iv;
     jss_cta_carve(sl, sm, c, iv);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = jss_warp_index(), lane = threadIdx.x & 31;
     JssWarpSmem w;
     jss_step_carve(sl, sm, warp, w);
     if (lane == 0) jss_mbar_init(w.mbar);

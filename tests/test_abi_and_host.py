@@ -124,3 +124,33 @@ def test_markstein_division_is_exact_for_all_bundled_divisors(tmp_path):
         args += [str(y), str(y)]
     r = subprocess.run([str(exe)] + args, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout[-400:]
+
+
+def test_step_kernels_compile_as_warp_convergent_code():
+    """SASS property of the built library: with the warp-uniformity hints (jss_uniform in csrc/jss_device.cuh) ptxas proves
+    the step / rollout / policy kernels warp-convergent, i.e. no collective is guarded by BRA.DIV + a WARPSYNC stub.  The
+    property is fragile (one branch on a value ptxas cannot classify brings all of them back), so it is pinned here.
+    The uniform 4-jobs-per-lane step kernel is excluded on purpose (measured slower with the hint, see jss_hint_flags)."""
+    import collections
+    import shutil
+    from jssenv_b200.build import build
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([tool, "-sass", build()], capture_output=True, text=True, check=True).stdout
+    div, cur = collections.Counter(), None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            div[cur] += 0
+        elif cur and "BRA.DIV" in line:
+            div[cur] += 1
+    hot = {k: v for k, v in div.items()
+           if k.startswith("_Z15jss_step_kernel") or k.startswith("_Z21jss_step_mixed_kernel") or k.startswith("_Z14jss_env_kernel")}
+    assert len(hot) == 12 + 6 + 12, sorted(hot)
+    excluded = {k for k in hot if k.startswith("_Z15jss_step_kernelILi4E")}
+    assert len(excluded) == 3
+    bad = {k: v for k, v in hot.items() if v and k not in excluded}
+    assert not bad, bad
+    assert all(hot[k] > 0 for k in excluded), "update jss_hint_flags / this test together"
