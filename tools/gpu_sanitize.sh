@@ -49,7 +49,7 @@ while not done:
     obs, r, done, _, _ = f.step(int(np.flatnonzero(obs["action_mask"])[0]))
 print("facade makespan", f.current_time_step)
 PY
-for tool in memcheck racecheck synccheck; do
+for tool in ${SAN_ONLY:-memcheck racecheck synccheck}; do
   timeout 900 compute-sanitizer --tool $tool python /tmp/san.py > gpurun_out/${T}_sanitizer_$tool.log 2>&1; echo "$tool rc=$?"
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|envs_error|facade" gpurun_out/${T}_sanitizer_$tool.log | tail -6
 done
