@@ -172,8 +172,15 @@ JSS_DEV void jss_bulk_load(jss_saddr_t smem_dst, const void *gmem_src, uint32_t 
 JSS_DEV void jss_mbar_wait(jss_saddr_t mbar, uint32_t phase) {
     uint32_t ok;
     do {
+        // non-blocking poll: test_wait returns at once, try_wait may park the warp for a scheduler time slice when the
+        // block has not landed yet (measured: test_wait 0.3-0.7 % faster on the uniform and mixed step kernels)
+#ifdef JSS_MBAR_TRY_WAIT
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(mbar), "r"(phase) : "memory");
+#else
+        asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(mbar), "r"(phase) : "memory");
+#endif
     } while (!ok);
 }
 JSS_DEV void jss_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
