@@ -68,8 +68,9 @@ struct EnvRegs {
 // cannot classify -- threadIdx.x >> 5, a word every lane loaded from the same shared-memory address -- and every
 // *_sync collective after it is compiled as "maybe diverged": UMOV + BRA.DIV + an out-of-line WARPSYNC stub per
 // collective, BSSY/BSYNC around each branch, nothing kept in uniform registers.  Passing the few truly uniform
-// inputs of an env-step through a lane-0 shuffle removes all of that (uniform ta80 step kernel: 30 BRA.DIV sites
-// -> 0, 2 496 -> 2 144 SASS instructions).
+// inputs of an env-step through a lane-0 shuffle removes all of that (mixed-batch step kernel: 75 BRA.DIV sites
+// -> 0, 7 344 -> 5 392 SASS instructions, 94 -> 85 us per launch; tests/test_abi_and_host.py pins the property).
+// The value MUST be the same in every lane -- the shuffle is a hint, not a broadcast of lane 0's opinion.
 JSS_DEV int jss_uniform(int v) {
 #ifdef JSS_NO_UNIFORM_HINTS
     return v;
