@@ -1319,7 +1319,7 @@ jss_step_kernel(const JssParams p, const JssLaunch a, const JssSmemLayout sl) {
 // (tile counts differ by at most one per class, the extras dithered across CTAs), so the launch is balanced without a
 // cost model, and walks them class by class -- three complete loops in sequence, so each lane class keeps the register
 // allocation of its stand-alone kernel.  All CTAs start with the 100-job class and move on at about the same time:
-// the CTAs that share an SM mostly execute the same 40-60 KB loop body (the three together are 120 KB, more than
+// the CTAs that share an SM mostly execute the same 20-35 KB loop body (the three together are 67-86 KB, more than
 // the instruction cache holds).  Instance tables are re-staged only when the instance changes.
 template <int SAMPLE, bool BIG>   // BIG: the batch contains instances with 129..256 jobs (a fourth, 8-jobs-per-lane body)
 __global__ void __launch_bounds__(JSS_WARPS_PER_CTA * 32, BIG ? 1 : JSS_MIN_CTAS)
