@@ -581,7 +581,7 @@ def main():
                 traffic_src = "offline: ncu --set full capture committed under profiles/ (" + tj.get("source", "traffic.json") + ")"
         except Exception:
             pass
-        kj = 1 if J <= 32 else (2 if J <= 64 else 4)
+        kj = 1 if J <= 32 else (2 if J <= 64 else (4 if J <= 128 else 8))
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
